@@ -1,0 +1,380 @@
+#!/usr/bin/env python
+"""bench.py — OH grid-cell predictions/sec of the B200 path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--grid 360]
+
+A *step* is one pass of the hot path over the whole C<grid> x 72-level slab: the dense feature
+matrix X[N x 27] (resident in HBM) -> tree-ensemble prediction -> 10**x * OHscale -> OH_ML, i.e.
+what `predict_OH_with_XGB` does per call after packing (OH_GridCompMod.F90:347-374, :1569).
+`value` times that with CUDA events on the library's stream (inputs resident); `e2e` times the
+same through the xgb_fortran_api C ABI (XGDMatrixCreateFromMat + XGBoosterPredict + XGDMatrixFree)
+from pinned HOST buffers, H2D / D2H inside the timed region; `run1` (extra) times the fused
+device-resident Run1 (feature assembly + predict + export transform + diagnostic partial sums).
+N > 1: columns are sharded over ranks (one process per GPU, no collective on the data path;
+the build-defined diagnostic is all-reduced over NCCL in the `run1` leg) — total work is fixed,
+so scaling is "strong".
+
+`--impl reference` times the reference's CPU algorithm (the libxgboost-1.6.0-equivalent oracle
+restatement, OpenMP over all host cores) on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+KM = 72
+NFEAT = 27
+ALGO_BYTES_PER_CELL = NFEAT * 4 + 4  # 27 float32 in + 1 float32 out
+BOOSTER = dict(n_trees=100, max_depth=18)  # "Depth18_eta1_100Trees", OH_GridCompMod.F90:224
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def booster_path():
+    """Seeded prod-like booster (100 trees, depth <= 18, 27 features); grown once and cached."""
+    from quickchem_b200 import synth, xgbmodel
+
+    d = os.path.join(ROOT, "build")
+    os.makedirs(d, exist_ok=True)
+    p = os.path.join(d, f"oh_booster_{BOOSTER['n_trees']}x{BOOSTER['max_depth']}.model")
+    if not os.path.exists(p):
+        t0 = time.time()
+        f = synth.prod_like_booster(**BOOSTER)
+        xgbmodel.write_legacy_binary(f, p + ".tmp%d" % os.getpid())
+        os.replace(p + ".tmp%d" % os.getpid(), p)
+        log(f"[bench] grew booster: {f.total_nodes()} nodes in {time.time() - t0:.0f}s -> {p}")
+    return p
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")  # fmt: skip
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)  # fmt: skip
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm, reasons, smax = [], set(), None
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                smax = float(r[1])
+                for nm, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            except (ValueError, IndexError):
+                pass
+        hi = [v for v in sm if smax and v > 0.5 * smax] or sm
+        return {"sm_mhz": statistics.median(hi) if hi else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
+                "samples": len(sm)}  # fmt: skip
+
+
+def shard_fields(grid, rank, world):
+    """This rank's contiguous column range of C<grid> (whole j-rows) and its synthetic fields."""
+    from quickchem_b200 import capi, synth
+
+    ncol_g = 6 * grid * grid
+    col0, ncol = capi.partition_columns(ncol_g, world, rank) if world > 1 else (0, ncol_g)
+    if ncol % grid or col0 % grid:  # keep AR(1) rows whole: split by j-rows instead
+        rows = 6 * grid
+        r0, r1 = rows * rank // world, rows * (rank + 1) // world
+        col0, ncol = r0 * grid, (r1 - r0) * grid
+    t0 = time.time()
+    f = synth.raw_fields(grid, seed=20220726 + grid + 1000 * rank, col0=col0, ncol=ncol)
+    log(f"[bench r{rank}] synthetic fields C{grid} cols [{col0},{col0 + ncol}) in {time.time() - t0:.0f}s")
+    return col0, ncol, f
+
+
+def run_reference(args):
+    """The reference's CPU algorithm (oracle restatement) on a bounded sample; rank 0 only."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import cpu as oracle
+    from quickchem_b200 import synth
+
+    oracle.build()
+    model = oracle.Model(booster_path())
+    grid = args.grid
+    nrows_j = max(1, min(6 * grid, args.ref_cols // grid))
+    f = synth.raw_fields(grid, seed=20220726 + grid, col0=0, ncol=nrows_j * grid)
+    r = oracle.run1(model, f, synth.MAPL, tropp_min=0.0, want_features=True)
+    X = np.ascontiguousarray(r["X"])
+    n = X.shape[0]
+    out = np.empty(n, np.float32)
+    cores = oracle.omp_threads()
+
+    def step():
+        p = model.predict(X)  # orc_dmatrix_from_mat + orc_predict (:347-356)
+        np.power(np.float32(10.0), p, out=out)  # :369
+
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = (time.perf_counter() - t0) / args.steps
+    v = n / dt
+    sample = f"{n} rows = first {nrows_j * grid} columns x {KM} levels of C{grid}, per step"
+    print(json.dumps({
+        "impl": "reference", "metric": "OH grid-cell predictions/sec", "value": v, "unit": "cells/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(grid, args.gpus),
+        "cpu_baseline": {"value": v, "unit": "cells/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": "cells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }), flush=True)  # fmt: skip
+
+
+def workload_config(grid, world):
+    return {"workload": f"C{grid}x{KM}L OH prediction, {6 * grid * grid * KM} cells, dense X[Nx27] f32",
+            "booster": f"{BOOSTER['n_trees']} trees, max depth {BOOSTER['max_depth']}, 27 features (synthetic, seeded)",
+            "sharding": f"{world} rank(s), contiguous column blocks, no halo",
+            "cache": "inputs (>= 0.75 GB per GPU) exceed the 126 MB L2; forest stays L2-resident by design"}  # fmt: skip
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="qcoh", choices=["qcoh", "reference"])
+    ap.add_argument("--grid", type=int, default=360, help="cubed-sphere C<grid> (BASELINE configs[2] = 360)")
+    ap.add_argument("--ref-cols", type=int, default=7200, help="columns in the CPU sample")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU-baseline time")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--param", action="append", default=[], help="name=value forwarded to qcoh_set_param")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "qcoh" else args.warmup
+
+    if args.impl == "reference":
+        return run_reference(args)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    import torch  # plumbing only: process group, barrier, max-over-ranks
+
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from quickchem_b200 import capi, synth
+
+    L = capi.lib()
+    capi.check(L.qcoh_set_device(local))
+    for kv in args.param:
+        k, v = kv.split("=")
+        capi.set_param(k, v)
+    if rank == 0:
+        booster_path()
+    if dist:
+        dist.barrier()
+    booster = capi.Booster(booster_path())
+    info = booster.info()
+
+    col0, ncol, fields = shard_fields(args.grid, rank, world)
+    ncell = ncol * KM
+    area = np.full(ncol, 5.1e14 / (6 * args.grid * args.grid), np.float32)
+    dev = {k: capi.DeviceArray(v) for k, v in fields.items()}
+    d_area = capi.DeviceArray(area)
+    # tropp_min = 0 Pa: the slab is all 72 levels, as BASELINE.json's cell counts require
+    oh = capi.OhRun1(booster, ncol, KM, synth.MAPL, tropp_min=0.0)
+    rin = oh.make_in(dev, area=d_area)
+    dX = capi.DMatrix.device(ncell, NFEAT)
+    xptr = capi.vp()
+    capi.check(L.qcoh_dmatrix_device_ptr(dX.handle, capi.C.byref(xptr)))
+    d_out = {n: capi.DeviceArray(ncell) for n in ("OH", "OH_boost")}
+    ro = capi.Run1Out()
+    ro.OH, ro.OH_boost, ro.X = d_out["OH"].ptr, d_out["OH_boost"].ptr, xptr
+    capi.check(L.qcoh_oh_run1(oh.handle, capi.C.byref(rin), capi.C.byref(ro)))
+    assert ro.k1 == 1, ro.k1
+    dX.seal()
+    ro.X = None
+    d_pred = capi.DeviceArray(ncell)
+
+    def barrier():
+        capi.synchronize()
+        if dist:
+            dist.barrier()
+        torch.cuda.synchronize() if world > 1 else None
+
+    def max_over_ranks(ms):
+        if not dist:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def timed(fn, steps, warm):
+        for _ in range(warm):
+            fn()
+        barrier()
+        n0 = capi.launch_count()
+        capi.timer_start()
+        for _ in range(steps):
+            fn()
+        ms = capi.timer_stop()
+        barrier()
+        return max_over_ranks(ms) / steps, capi.launch_count() - n0
+
+    total_cells = 6 * args.grid * args.grid * KM
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+
+    # ---- value: predict step on the resident matrix (K2 + fused export transform)
+    step = lambda: booster.predict_device(dX, d_pred, exp10=True, scale=0.85)
+    ms_step, launches = timed(step, args.steps, args.warmup)
+    clocks = sampler.stop() if rank == 0 else None
+    value = total_cells / (ms_step * 1e-3)
+
+    # ---- run1: fused device-resident Run1 (+ NCCL all-reduce of the diagnostic at N > 1)
+    diag_t = torch.zeros(4, dtype=torch.float64, device="cuda") if dist else None
+
+    def run1_step():
+        capi.check(L.qcoh_oh_run1(oh.handle, capi.C.byref(rin), capi.C.byref(ro)))
+        if dist:
+            diag_t.copy_(torch.tensor(list(ro.diag), dtype=torch.float64))
+            dist.all_reduce(diag_t)
+
+    def wall(fn, steps, warm):
+        for _ in range(warm):
+            fn()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            fn()
+        capi.synchronize()
+        dt = (time.perf_counter() - t0) * 1e3
+        barrier()
+        return max_over_ranks(dt) / steps
+
+    ms_run1 = wall(run1_step, max(3, args.steps // 2), 2)
+    diag = list(ro.diag) if not dist else diag_t.tolist()
+
+    # ---- e2e: xgb_fortran_api C ABI from pinned host buffers
+    e2e = None
+    if not args.no_e2e:
+        hX = capi.pinned_empty((ncell, NFEAT))
+        capi.check(L.qcoh_memcpy_d2h(hX.ctypes.data_as(capi.vp), xptr, hX.nbytes))
+        sink = np.zeros(1, np.float64)
+
+        def e2e_step():
+            d = capi.DMatrix(hX, -999.0)             # XGDMatrixCreateFromMat_f (:347)  H2D
+            n, p = booster.predict_raw(d)            # XGBoosterPredict_f (:356)        kernel + D2H
+            res = np.ctypeslib.as_array(p, (n,))
+            sink[0] = float(res[0]) + float(res[n - 1])  # the host reads the result it was handed
+            d.free()                                 # XGDMatrixFree_f (:377)
+
+        ms_e2e = wall(e2e_step, max(3, args.steps // 2), 2)
+        e2e = {"value": total_cells / (ms_e2e * 1e-3), "unit": "cells/s", "h2d_bytes_per_step": ncell * NFEAT * 4 * world,
+               "d2h_bytes_per_step": ncell * 4 * world, "ms_per_step": ms_e2e,
+               "path": "XGDMatrixCreateFromMat+XGBoosterPredict+XGDMatrixFree, pinned host X, result read on host"}  # fmt: skip
+
+    # ---- cpu_baseline: oracle on a bounded sample of the same X (rank 0, N = 1 only)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        from oracle import cpu as oracle
+
+        oracle.build()
+        om = oracle.Model(booster_path())
+        hs = np.empty((1 << 18, NFEAT), np.float32)
+        stride = max(1, ncell // hs.shape[0])
+        probe_rows = np.arange(hs.shape[0]) * stride
+        full = capi.pinned_empty((ncell, NFEAT)) if args.no_e2e else hX
+        if args.no_e2e:
+            capi.check(L.qcoh_memcpy_d2h(full.ctypes.data_as(capi.vp), xptr, full.nbytes))
+        hs[:] = full[probe_rows]
+        t0 = time.perf_counter()
+        ref_probe = om.predict(hs)
+        probe_dt = time.perf_counter() - t0
+        nsamp = int(min(ncell, max(hs.shape[0], hs.shape[0] * args.cpu_seconds / max(probe_dt, 1e-3))))
+        nsamp = min(nsamp, 1 << 25)
+        stride = max(1, ncell // nsamp)
+        rows = np.arange(nsamp) * stride
+        xs = np.ascontiguousarray(full[rows])
+        t0 = time.perf_counter()
+        ref = om.predict(xs)
+        oh_ref = np.power(np.float32(10.0), ref) * np.float32(0.85)
+        cpu_dt = time.perf_counter() - t0
+        # the same rows on the GPU must agree with the CPU baseline (parity spot check)
+        got = d_pred.get()[rows]
+        rel = float(np.max(np.abs(got.astype(np.float64) - oh_ref) / np.abs(oh_ref)))
+        cpu = {"value": nsamp / cpu_dt, "unit": "cells/s", "cores": oracle.omp_threads(), "kind": "port",
+               "sample": f"{nsamp} rows (every {stride}th row of the C{args.grid}x{KM} matrix): dense->CSR + predict + 10**x",
+               "seconds": cpu_dt, "max_rel_err_gpu_vs_cpu": rel}  # fmt: skip
+
+    if rank != 0:
+        if dist:
+            dist.destroy_process_group()
+        return
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except OSError:
+        pass
+    peak = peaks.get("hbm_gbs", 6650.0)
+    achieved = (ncell * ALGO_BYTES_PER_CELL / 1e9) / (ms_step * 1e-3)  # per GPU: this rank's launch
+    visits = None
+    out = {
+        "metric": "OH grid-cell predictions/sec", "value": value, "unit": "cells/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args.grid, world),
+        "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
+        "roofline": {"bound": "hbm", "kernel": "predict_rows_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": None,
+                     "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured copy)" if peaks else "fallback 6.65 TB/s",
+                     "algorithmic_bytes_per_cell": ALGO_BYTES_PER_CELL, "cells_per_launch": ncell,
+                     "note": "traversal is bound by node gathers / issue slots, not HBM (DESIGN.md)"},
+        "cpu_baseline": cpu,
+        "run1": {"value": total_cells / (ms_run1 * 1e-3), "unit": "cells/s", "ms_per_step": ms_run1,
+                 "what": "fused device-resident Run1: assembly + predict + export transform + diagnostic"
+                         + (" + NCCL all-reduce" if dist else ""),
+                 "global_mean_oh_molec_cm3": diag[0] / diag[1] if diag[1] else None,
+                 "ch4_lifetime_years": diag[2] / diag[3] / 3.15576e7 if diag[3] else None},
+        "booster": {"trees": info.num_trees, "nodes": int(info.num_nodes), "max_depth": info.max_depth},
+    }  # fmt: skip
+    print(json.dumps(out), flush=True)
+    if dist:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

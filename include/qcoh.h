@@ -1,0 +1,224 @@
+/* qcoh.h — C ABI of libqcoh.so, the B200 (sm_100a) replacement for the one hot path of
+ * GEOS-ESM/QuickChem: per-grid-cell OH prediction (OH_GridComp -> xgb_fortran_api -> libxgboost).
+ *
+ * Two groups of entry points:
+ *
+ *  (1) The eleven XGBoost-named symbols that the reference's Fortran interface module binds
+ *      (/root/reference/Shared/xgb_fortran_api.F90:18-120).  Same names, argument meaning,
+ *      ownership and 0 / -1 return convention as libxgboost 1.6.0, so the reference's
+ *      `predict_OH_with_XGB` (OH_GridComp/OH_GridCompMod.F90:123-398) links against libqcoh.so
+ *      unchanged.  Everything numerical runs on the GPU; there is no CPU fallback: without a
+ *      CUDA device every compute call returns -1 and XGBGetLastError() says why.
+ *
+ *  (2) qcoh_* — the device-resident, fused extension a patched Run1 calls
+ *      (OH_GridCompMod.F90:1232-1599): feature assembly, prediction, export transform and the
+ *      build-defined global-mean diagnostic without ever forming the [N x 27] matrix on the host.
+ *
+ * Plain pointers and sizes only.  Thread model: one host thread per process per GPU (as the
+ * reference: `SAVE` booster, OH_GridCompMod.F90:182,209); the last-error string is thread-local.
+ */
+#ifndef QCOH_H
+#define QCOH_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void *DMatrixHandle;
+typedef void *BoosterHandle;
+typedef uint64_t bst_ulong;
+
+/* =====================================================================================
+ * (1) xgb_fortran_api boundary
+ * ================================================================================== */
+
+/* replaces libxgboost XGBoosterLoadModel — xgb_fortran_api.F90:18-24 (wrapper :123-131);
+ * call site OH_GridCompMod.F90:261.  Reads XGBoost legacy binary ("binf" optional; what
+ * `*.model` / `*.bin` of OH_instance_OH.rc:17-20 are), JSON and UBJSON; flattens the trees
+ * into the depth-ordered device layout and uploads them once. */
+int XGBoosterLoadModel(BoosterHandle handle, const char *fname);
+
+/* xgb_fortran_api.F90:26-32 (wrapper :133-141).  Unused by OH.  Writes legacy binary, or
+ * JSON / UBJSON when fname ends in .json / .ubj (libxgboost 1.6.0 rule). */
+int XGBoosterSaveModel(BoosterHandle handle, const char *fname);
+
+/* xgb_fortran_api.F90:34-41 (wrapper :143-152).  Unused by OH.  Writes the dense matrix in
+ * libqcoh's own container ("QCDM" magic), readable by XGDMatrixCreateFromFile below. */
+int XGDMatrixSaveBinary(DMatrixHandle handle, const char *fname, int silent);
+
+/* xgb_fortran_api.F90:44-49 (wrapper :156-161); call sites OH_GridCompMod.F90:264,377. */
+int XGDMatrixFree(DMatrixHandle handle);
+
+/* xgb_fortran_api.F90:52-59 (wrapper :165-174).  Unused by OH.  Reads a "QCDM" file. */
+int XGDMatrixCreateFromFile(const char *fname, int silent, DMatrixHandle *out);
+
+/* xgb_fortran_api.F90:61-73; call site OH_GridCompMod.F90:356 (option_mask=0, ntree_limit=0,
+ * training=0).  option_mask: 0 value, 1 margin, 2 leaf index per tree ([nrow][ntree] floats).
+ * *out_result points at a pinned host buffer owned by the booster, valid until the next
+ * predict / free on that booster (libxgboost's thread-local-entry contract). */
+int XGBoosterPredict(BoosterHandle handle, DMatrixHandle dmat, int option_mask, unsigned ntree_limit,
+                     int training, bst_ulong *out_len, const float **out_result);
+
+/* xgb_fortran_api.F90:75-83; call site OH_GridCompMod.F90:256.  The reference passes a DMatrix
+ * handle *by value* as `dmats` with len = 0; dmats is never dereferenced when len == 0. */
+int XGBoosterCreate(const DMatrixHandle dmats[], bst_ulong len, BoosterHandle *out);
+
+/* xgb_fortran_api.F90:85-95; call sites OH_GridCompMod.F90:251,347 (missing = -999.0).
+ * data is row-major [nrow][ncol] HOST memory (or device memory: detected), borrowed for the
+ * call only.  Entries that are NaN or == missing are missing; +-inf with a finite `missing`
+ * fails like libxgboost.  The matrix is copied to HBM here. */
+int XGDMatrixCreateFromMat(const float *data, bst_ulong nrow, bst_ulong ncol, float missing,
+                           DMatrixHandle *out);
+
+/* xgb_fortran_api.F90:97-104 and :106-113.  Unused by OH. */
+int XGDMatrixNumRow(DMatrixHandle handle, bst_ulong *out);
+int XGDMatrixNumCol(DMatrixHandle handle, bst_ulong *out);
+
+/* xgb_fortran_api.F90:115-120.  Commented out at OH_GridCompMod.F90:389-392. */
+int XGBoosterFree(BoosterHandle handle);
+
+/* libxgboost's error channel (not bound by xgb_fortran_api, but part of the same C API). */
+const char *XGBGetLastError(void);
+
+/* =====================================================================================
+ * (2) qcoh_* extension
+ * ================================================================================== */
+
+/* ---- library / device -------------------------------------------------------------- */
+const char *qcoh_version(void);
+/* Number of visible CUDA devices (0 without a GPU; never fails). */
+int qcoh_device_count(void);
+/* Bind this process to one GPU (one process per GPU; default = $LOCAL_RANK or 0). */
+int qcoh_set_device(int device);
+/* Pinned host memory for callers that want full-speed H2D/D2H (cudaHostAlloc / cudaFreeHost). */
+int qcoh_host_alloc(size_t bytes, void **out);
+int qcoh_host_free(void *p);
+/* Raw device memory + copies, so that a Fortran/C host can keep fields resident in HBM. */
+int qcoh_device_alloc(size_t bytes, void **out);
+int qcoh_device_free(void *p);
+int qcoh_memcpy_h2d(void *dst_dev, const void *src_host, size_t bytes);
+int qcoh_memcpy_d2h(void *dst_host, const void *src_dev, size_t bytes);
+int qcoh_device_synchronize(void);
+/* Device-side timing of library work (CUDA events on the library's stream). */
+int qcoh_timer_start(void);
+int qcoh_timer_stop(float *elapsed_ms);
+/* Overwrite a > L2-sized scratch buffer (cache flush between timed iterations). */
+int qcoh_flush_l2(void);
+
+/* ---- booster introspection (host side only; works without a GPU) -------------------- */
+typedef struct {
+  int32_t num_trees;
+  int32_t num_feature;
+  int32_t max_depth;       /* deepest leaf over all trees */
+  int64_t num_nodes;       /* total nodes */
+  float base_score;
+  int32_t format;          /* 0 legacy binary, 1 JSON, 2 UBJSON */
+  uint32_t version[3];
+} qcoh_booster_info;
+/* Parse a model file into a booster WITHOUT touching the GPU (upload happens lazily at the
+ * first predict).  XGBoosterLoadModel == this + upload. */
+int qcoh_booster_parse(BoosterHandle handle, const char *fname);
+int qcoh_booster_get_info(BoosterHandle handle, qcoh_booster_info *out);
+/* Flattened depth-ordered layout, for inspection/tests: 8-byte nodes {uint32 value_bits;
+ * uint32 meta}, see DESIGN.md "Node layout".  tree_offset has num_trees+1 entries. */
+int qcoh_booster_get_flat(BoosterHandle handle, const uint32_t **nodes_xy, const uint32_t **tree_offset,
+                          const int32_t **tree_depth, const int32_t **orig_id);
+
+/* ---- device-resident predict -------------------------------------------------------- */
+/* A DMatrix whose storage is allocated in HBM and filled by the caller (device pointer
+ * returned by qcoh_dmatrix_device_ptr) or by qcoh_dmatrix_upload.  Call qcoh_dmatrix_seal
+ * after filling: it runs the missing / inf scan XGDMatrixCreateFromMat would have run. */
+int qcoh_dmatrix_create_device(bst_ulong nrow, bst_ulong ncol, float missing, DMatrixHandle *out);
+int qcoh_dmatrix_device_ptr(DMatrixHandle handle, float **out_dev);
+int qcoh_dmatrix_upload(DMatrixHandle handle, const float *host_rows, bst_ulong row0, bst_ulong nrows);
+int qcoh_dmatrix_seal(DMatrixHandle handle);
+
+/* Export transform fused into the predict kernel's epilogue (OH_GridCompMod.F90:369,1569):
+ * out = scale * 10**pred when exp10 != 0, else the raw prediction. */
+typedef struct {
+  int exp10;      /* 1: apply 10.0**x (OH_GridCompMod.F90:369) */
+  float scale;    /* OHscale (OH_GridCompMod.F90:1569); 1.0 = none */
+} qcoh_epilogue;
+/* Predict into a DEVICE buffer (nrow floats, or nrow*ntree for option_mask 2).  No host copy.
+ * epi may be NULL.  Asynchronous on the library stream; qcoh_device_synchronize() to wait. */
+int qcoh_booster_predict_device(BoosterHandle handle, DMatrixHandle dmat, int option_mask,
+                                unsigned ntree_limit, const qcoh_epilogue *epi, float *out_dev);
+/* Kernel variant selection for experiments / profiling (0 = default).  See DESIGN.md. */
+int qcoh_set_param(const char *name, const char *value);
+/* How many kernels the library has launched since load (for bench.py's gpu_launches). */
+uint64_t qcoh_launch_count(void);
+
+/* ---- fused Run1 (feature assembly -> predict -> export transform) -------------------- */
+typedef void *qcoh_oh_handle;
+
+/* Static configuration: OH_GridComp state + MAPL constants (OH_GridCompMod.F90:48-80,547-567;
+ * MAPL constants are external to the reference and therefore passed in, not hard-coded). */
+typedef struct {
+  int ncol;                 /* local columns im*jm, i fastest */
+  int km;                   /* levels */
+  float mapl_epsilon, mapl_avogad, mapl_runiv, mapl_radians_to_degrees, mapl_degrees_to_radians;
+  float ohscale;            /* OH_instance_OH.rc:42 */
+  int compute_once_per_day; /* OH_instance_OH.rc:38; dynamic_k_range = !this (:1561) */
+  float tropp_min;          /* 4000 Pa (:1563) */
+  float missing;            /* -999.0 (:213) */
+} qcoh_oh_config;
+
+/* Per-step inputs.  Every pointer may be HOST or DEVICE memory (detected per pointer); host
+ * fields are copied to resident HBM buffers, device fields are used in place.  Layout: 3-D
+ * centre fields [km][ncol], edge fields (PLE, ZLE) [km+1][ncol], 2-D fields [ncol] — the
+ * Fortran (im,jm,km) arrays as they lie in memory. */
+typedef struct {
+  int nymd;                 /* yyyymmdd, for JulianDay (:1481) */
+  int need_to_call_boost;   /* :1189-1193; 0 => reuse the persistent OH_ML (:76-78) */
+  /* current model state, :1233-1236 */
+  const float *T_MOD, *Q_MOD, *PLE_MOD, *TROPP;
+  /* values handed to boost, selected per OH_data_source by the caller (:1326-1436,1493-1540) */
+  const float *T_BST, *Q_BST, *PLE_BST, *ZLE_BST;
+  const float *TAUCLW, *TAUCLI, *FCLD, *CH4, *CO;
+  const float *SCA[7];      /* BC OC BR DU SU SS NI scattering coefficients at wavelength_index */
+  const float *NO2, *O3, *ISOP, *ACET, *C2H6, *C3H8, *PRPE, *ALK4, *MP, *H2O2, *CH2O;
+  const float *GMITO3, *GMITTO3, *ALBUV, *LATS, *LONS;
+  const float *OH_CLIM;     /* oh_OH (default OH above the tropopause, :1548,1584) */
+  /* optional inputs of the build-defined diagnostic (not in the reference) */
+  const float *AREA;        /* [ncol] m2, may be NULL */
+} qcoh_run1_in;
+
+/* Outputs; NULL = not wanted.  HOST or DEVICE pointers. */
+typedef struct {
+  float *OH;        /* [km][ncol] molec/cm3 — internal state OH (:1595) */
+  float *OH_boost;  /* [km][ncol] mol/mol — export OH_boost (:1571-1572) */
+  float *NDWET;     /* [km][ncol] — export DIAG_NDWET (:1598-1599) */
+  float *X;         /* [ncol*ksub][27] assembled feature matrix (debug / parity) */
+  float *pred;      /* [ncol*ksub] raw booster output (debug / parity) */
+  int k1;           /* out: first predicted level, 1-based (k2 = km), :300-301 */
+  /* build-defined diagnostic, local partial sums (float64): sum(OH*w), sum(w),
+   * sum(nCH4*V), sum(k(T)*OH*nCH4*V); valid when AREA != NULL */
+  double diag[4];
+} qcoh_run1_out;
+
+int qcoh_oh_create(BoosterHandle booster, const qcoh_oh_config *cfg, qcoh_oh_handle *out);
+int qcoh_oh_run1(qcoh_oh_handle h, const qcoh_run1_in *in, qcoh_run1_out *out);
+int qcoh_oh_free(qcoh_oh_handle h);
+
+/* ---- host mirror of the reference driver -------------------------------------------- */
+/* C mirror of `predict_OH_with_XGB` (OH_GridCompMod.F90:123-398): same arguments in the same
+ * order, arrays as Fortran lays them out; bb = the 27 OH_BOOST_INPUT_DATA pointers (:82-114) in
+ * feature order, is2d[f] != 0 for the (i,j) members.  Goes ONLY through the eleven XGBoost-named
+ * symbols above — it is what the unmodified Fortran does, restated in C for hosts without a
+ * Fortran compiler — and keeps the booster in static storage like the reference's SAVE. */
+int qcoh_predict_OH_with_XGB(const char *xgb_fname, int icount, int jcount, int kcount,
+                             int dynamic_k_range, float tropp_min, const float *pl, const float *tropp,
+                             const float *const bb[27], const int is2d[27], float *OH_ML);
+/* Drop the static booster of the mirror (tests). */
+void qcoh_predict_OH_reset(void);
+
+/* ---- sharding across GPUs -------------------------------------------- */
+/* Contiguous, near-equal split of `ncol_global` columns over `nranks`; no halo. */
+int qcoh_partition_columns(int64_t ncol_global, int nranks, int rank, int64_t *col0, int64_t *ncol_local);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QCOH_H */

@@ -71,6 +71,7 @@ def lib():
     if _LIB is None:
         L = C.CDLL(build())
         L.orc_last_error.restype = C.c_char_p
+        L.orc_num_threads.restype = C.c_int
         L.orc_model_load.restype = C.POINTER(_Model)
         L.orc_model_load.argtypes = [C.c_char_p]
         L.orc_model_free.argtypes = [C.POINTER(_Model)]
@@ -145,6 +146,10 @@ class Model:
         return out.reshape(nrow, nt) if option_mask & 2 else out
 
 
+def omp_threads() -> int:
+    return lib().orc_num_threads()
+
+
 def julian_day(nymd):
     return lib().orc_julian_day(nymd)
 
@@ -175,7 +180,7 @@ def run1(model: Model, fields: dict, consts: dict, *, ohscale=0.85, compute_once
     i.mapl_epsilon, i.mapl_avogad, i.mapl_runiv = consts["EPSILON"], consts["AVOGAD"], consts["RUNIV"]
     i.mapl_radians_to_degrees, i.mapl_degrees_to_radians = consts["RADIANS_TO_DEGREES"], consts["DEGREES_TO_RADIANS"]
     i.ohscale, i.compute_once_per_day, i.tropp_min, i.nymd, i.missing = ohscale, int(compute_once_per_day), tropp_min, nymd, missing
-    i.T_MOD, i.Q_MOD, i.PLE_MOD, i.TROPP = P(mod["T"]), P(mod["Q"]), P(mod["PLE"]), P(fields["TROPP"])
+    i.T_MOD, i.Q_MOD, i.PLE_MOD, i.TROPP = P(mod["T"]), P(mod["Q"]), P(mod["PLE"]), P(mod["TROPP"])
     i.T_BST, i.Q_BST, i.PLE_BST, i.ZLE_BST = P(fields["T"]), P(fields["Q"]), P(fields["PLE"]), P(fields["ZLE"])
     i.TAUCLW, i.TAUCLI, i.FCLD, i.CH4, i.CO = (P(fields[k]) for k in ("TAUCLW", "TAUCLI", "FCLD", "CH4", "CO"))
     for s, sp in enumerate(("BC", "OC", "BR", "DU", "SU", "SS", "NI")):

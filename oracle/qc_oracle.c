@@ -13,6 +13,13 @@
 
 static _Thread_local char g_err[512];
 const char *orc_last_error(void) { return g_err; }
+int orc_num_threads(void) {
+#ifdef _OPENMP
+  return omp_get_max_threads();
+#else
+  return 1;
+#endif
+}
 #define FAIL(ret, ...)                          \
   do {                                          \
     snprintf(g_err, sizeof g_err, __VA_ARGS__); \

@@ -63,6 +63,7 @@ typedef struct {
 } orc_dmatrix;
 
 const char *orc_last_error(void);
+int orc_num_threads(void); /* OpenMP threads the predictor uses */
 
 /* XGBoosterLoadModel restatement, legacy binary ("binf" optional) only. */
 orc_model *orc_model_load(const char *path);

@@ -1,0 +1,64 @@
+// forest.hpp — host-side booster: XGBoost model files -> in-memory trees -> flattened,
+// depth-ordered structure-of-nodes that the sm_100a predict kernel walks.
+//
+// Replaces what `XGBoosterLoadModel` does inside libxgboost 1.6.0 for the reference
+// (/root/reference/OH_GridComp/OH_GridCompMod.F90:261 via Shared/xgb_fortran_api.F90:18-24).
+// Pure C++ (no CUDA), so it is testable on a box without a GPU.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+namespace qcoh {
+
+// One tree as XGBoost stores it (RegTree::Node + RTreeNodeStat), node 0 = root.
+struct HostTree {
+  std::vector<int32_t> cleft, cright, parent;  // parent: raw legacy encoding (bit31 = is-left-child, -1 root)
+  std::vector<uint32_t> sindex;                // bit31 default_left | split feature
+  std::vector<float> info;                     // split_cond, or leaf_value at leaves
+  std::vector<float> loss_chg, sum_hess, base_weight;
+  std::vector<int32_t> leaf_child_cnt;
+  int32_t num_nodes() const { return (int32_t)cleft.size(); }
+};
+
+enum ModelFormat { kLegacyBinary = 0, kJson = 1, kUbjson = 2 };
+
+struct HostForest {
+  float base_score = 0.5f;
+  uint32_t num_feature = 0;
+  uint32_t version[3] = {1, 6, 0};
+  std::string objective = "reg:squarederror";
+  std::vector<HostTree> trees;
+  std::vector<int32_t> tree_info;
+  std::vector<std::pair<std::string, std::string>> attributes;
+  ModelFormat format = kLegacyBinary;
+};
+
+// Flattened layout (see DESIGN.md "Node layout").  Per tree the nodes are renumbered in
+// breadth-first (depth) order, siblings adjacent (right = left + 1).  One node = 8 bytes:
+//   x: float bits — split threshold, or the leaf value at a leaf
+//   y: meta = feat << 24 | default_left << 23 | rel   (rel = left-child index - own index)
+// A leaf has rel = 0 and feat = num_feature: the predict kernel keeps one extra per-row
+// slot holding -inf at that feature index, so `!(v < x)` is false and the walk self-loops
+// without a leaf test.
+constexpr uint32_t kMetaFeatShift = 24;
+constexpr uint32_t kMetaDefaultLeftBit = 1u << 23;
+constexpr uint32_t kMetaRelMask = (1u << 23) - 1;
+constexpr uint32_t kMaxFeatures = 254;
+
+struct FlatForest {
+  std::vector<uint32_t> nodes_xy;     // 2 words per node
+  std::vector<uint32_t> tree_offset;  // [ntree + 1], in nodes
+  std::vector<int32_t> tree_depth;    // [ntree] depth of the deepest leaf (root = 0)
+  std::vector<int32_t> orig_id;       // flattened position -> XGBoost node id (pred_leaf output)
+  int32_t max_depth = 0;
+  int64_t num_nodes() const { return (int64_t)orig_id.size(); }
+};
+
+// Throws std::runtime_error with libxgboost-style messages on malformed / unsupported input.
+HostForest load_model_file(const std::string &path);
+HostForest load_model_buffer(const unsigned char *buf, size_t len);
+void save_model_file(const HostForest &f, const std::string &path);
+FlatForest flatten(const HostForest &f);
+
+}  // namespace qcoh

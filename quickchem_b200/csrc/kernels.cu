@@ -1,0 +1,436 @@
+// kernels.cu — hand-written sm_100a kernels of the OH hot path.
+//
+//   K2  predict_rows_kernel   tree-ensemble traversal, replaces libxgboost's CPUPredictor behind
+//                             XGBoosterPredict (reference call site OH_GridCompMod.F90:356) with the
+//                             export transform 10**x * OHscale (:369,:1569) fused as epilogue
+//   K3  scan_matrix_kernel    the missing / inf scan of XGDMatrixCreateFromMat (:347)
+//   K1  oh_state / oh_sums / oh_pack    Run1 feature assembly (:1240-1257, :1441-1488, :303-345)
+//   K5  oh_finalize           troposphere mask + unit conversion (:1579-1595)
+//   K4  oh_diag               build-defined mass-weighted mean OH / CH4 lifetime partial sums
+//
+// Numerics: compiled with -fmad=false and written with explicit round-to-nearest intrinsics where
+// the Fortran evaluation order matters, so every float32 feature is bit-identical to the CPU
+// evaluation.  No tensor cores: tree traversal is not a dense contraction.
+#include "kernels.hpp"
+
+#include <cfloat>
+#include <cmath>
+
+#include "forest.hpp"
+
+namespace qcoh {
+
+static uint64_t g_launches = 0;
+uint64_t launch_count() { return g_launches; }
+
+#define QC_LAUNCHED() (++g_launches, cudaGetLastError())
+
+// =====================================================================================
+// K3 — matrix scan
+// =====================================================================================
+__global__ void __launch_bounds__(256) scan_matrix_kernel(const float *__restrict__ X, uint64_t n, float missing,
+                                                          int check_inf, int *flags) {
+  int f = 0;
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const float v = __ldg(X + i);
+    if (v != v || v == missing) f |= 1;
+    if (check_inf && isinf(v)) f |= 2;
+  }
+  f = __reduce_or_sync(0xffffffffu, f);
+  if ((threadIdx.x & 31) == 0 && f) atomicOr(flags, f);
+}
+
+cudaError_t launch_scan_matrix(const float *X, uint64_t n, float missing, int *flags, cudaStream_t s) {
+  if (n == 0) return cudaSuccess;
+  int blocks = (int)((n + 255) / 256 < 148 * 16 ? (n + 255) / 256 : 148 * 16);
+  // xgboost src/data/data.cc: `!std::isinf(missing) && std::isinf(value)` invalidates the input
+  scan_matrix_kernel<<<blocks, 256, 0, s>>>(X, n, missing, std::isinf(missing) ? 0 : 1, flags);
+  return QC_LAUNCHED();
+}
+
+__global__ void fill_kernel(float *p, uint64_t n, float v) {
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) p[i] = v;
+}
+cudaError_t launch_fill(float *p, uint64_t n, float v, cudaStream_t s) {
+  if (n == 0) return cudaSuccess;
+  int blocks = (int)((n + 255) / 256 < 148 * 16 ? (n + 255) / 256 : 148 * 16);
+  fill_kernel<<<blocks, 256, 0, s>>>(p, n, v);
+  return QC_LAUNCHED();
+}
+
+// =====================================================================================
+// K2 — predict
+// =====================================================================================
+// One thread = one row (grid cell).  The CTA's rows are staged in shared memory as
+// srow[row][S] with S odd (bank = (row*S + f) mod 32 is a bijection over a warp's 32 rows, so
+// the data-dependent feature fetch never bank-conflicts).  Slot `nfeat` of every row holds
+// -inf: leaves are encoded with feat = nfeat and rel = 0, so `!(v < x)` is false there and the
+// walk self-loops — the descent is a fixed-trip-count loop with no leaf test and no divergent
+// branch.  Missing entries (NaN or == missing) are canonicalised to NaN while staging.
+//
+// XGBoost semantics restated (xgboost 1.6.0 src/predictor/predict_fn.h GetNextNode,
+// src/predictor/cpu_predictor.cc PredictByAllTrees): missing -> default child, else
+// left + !(fvalue < split_cond); out = base_score, then += leaf value tree by tree in float32.
+template <int ILP, bool HAS_MISSING>
+__device__ __forceinline__ void walk_group(const uint2 *__restrict__ nodes, const uint32_t *__restrict__ toff,
+                                           const int32_t *__restrict__ tdepth, int t, const float *my,
+                                           uint32_t (&idx)[ILP], uint32_t (&xbits)[ILP]) {
+  int depth = 0;
+#pragma unroll
+  for (int j = 0; j < ILP; ++j) {
+    idx[j] = __ldg(toff + t + j);
+    depth = max(depth, __ldg(tdepth + t + j));
+    xbits[j] = 0;
+  }
+  // depth + 1 fetches: the last one reads the leaf itself, whose x word is the leaf value
+  for (int d = 0; d <= depth; ++d) {
+#pragma unroll
+    for (int j = 0; j < ILP; ++j) {
+      const uint2 nd = __ldg(nodes + idx[j]);
+      const float v = my[nd.y >> kMetaFeatShift];
+      bool right = !(v < __uint_as_float(nd.x));
+      if (HAS_MISSING) {
+        if (v != v) right = !(nd.y & kMetaDefaultLeftBit);
+      }
+      idx[j] += (nd.y & kMetaRelMask) + (right ? 1u : 0u);
+      xbits[j] = nd.x;
+    }
+  }
+}
+
+__device__ __forceinline__ float export_transform(float acc, int exp10_on, float scale) {
+  if (!exp10_on) return acc;
+  // OH_ML = 10.0 ** pred (OH_GridCompMod.F90:369), then OH_ML * OHscale (:1569): two float32
+  // roundings.  10**x is evaluated in float64 and rounded once (SURVEY.md hard part 7).
+  const float p = (float)exp10((double)acc);
+  return __fmul_rn(p, scale);
+}
+
+template <int ILP, bool HAS_MISSING, bool PRED_LEAF>
+__global__ void __launch_bounds__(256) predict_rows_kernel(DeviceForest f, PredictArgs a, int S) {
+  extern __shared__ float srow[];
+  const int tid = threadIdx.x;
+  const uint64_t r0 = (uint64_t)blockIdx.x * blockDim.x;
+  const uint64_t left = a.nrow - r0;
+  const int nr = left < (uint64_t)blockDim.x ? (int)left : (int)blockDim.x;
+  const int ncol = a.ncol;
+  {
+    const float *__restrict__ src = a.X + r0 * (uint64_t)ncol;
+    const int n = nr * ncol;
+    const float qnan = __int_as_float(0x7fc00000);
+    for (int i = tid; i < n; i += blockDim.x) {
+      const int row = i / ncol;
+      const int col = i - row * ncol;
+      float v = __ldg(src + i);
+      if (HAS_MISSING && v == a.missing) v = qnan;
+      srow[row * S + col] = v;
+    }
+    // columns the matrix does not have are missing (xgboost FVec::Fill leaves them flagged)
+    for (int c = ncol; c < f.nfeat; ++c) srow[tid * S + c] = qnan;
+    srow[tid * S + f.nfeat] = -INFINITY;
+  }
+  __syncthreads();
+  if (tid >= nr) return;
+  const float *my = srow + tid * S;
+  const uint64_t row = r0 + tid;
+  const int ntree = a.ntree_used;
+  float acc = f.base_score;
+  int t = 0;
+  for (; t + ILP <= ntree; t += ILP) {
+    uint32_t idx[ILP], xb[ILP];
+    walk_group<ILP, HAS_MISSING>(f.nodes, f.tree_offset, f.tree_depth, t, my, idx, xb);
+#pragma unroll
+    for (int j = 0; j < ILP; ++j) {
+      if (PRED_LEAF)
+        a.out[row * (uint64_t)ntree + t + j] = (float)__ldg(f.orig_id + idx[j]);
+      else
+        acc = __fadd_rn(acc, __uint_as_float(xb[j]));
+    }
+  }
+  for (; t < ntree; ++t) {
+    uint32_t idx[1], xb[1];
+    walk_group<1, HAS_MISSING>(f.nodes, f.tree_offset, f.tree_depth, t, my, idx, xb);
+    if (PRED_LEAF)
+      a.out[row * (uint64_t)ntree + t] = (float)__ldg(f.orig_id + idx[0]);
+    else
+      acc = __fadd_rn(acc, __uint_as_float(xb[0]));
+  }
+  if (!PRED_LEAF) a.out[row] = export_transform(acc, a.exp10, a.scale);
+}
+
+template <int ILP>
+static cudaError_t launch_predict_ilp(const DeviceForest &f, const PredictArgs &a, int block, cudaStream_t s) {
+  const int S = (f.nfeat + 1) | 1;
+  const size_t smem = (size_t)block * S * sizeof(float);
+  const uint64_t nblk = (a.nrow + block - 1) / block;
+  if (nblk > 0x7fffffffull) return cudaErrorInvalidConfiguration;
+  const dim3 grid((unsigned)nblk);
+#define QC_GO(HM, PL)                                                                                            \
+  do {                                                                                                           \
+    auto k = predict_rows_kernel<ILP, HM, PL>;                                                                   \
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);             \
+    if (e != cudaSuccess) return e;                                                                              \
+    k<<<grid, block, smem, s>>>(f, a, S);                                                                        \
+  } while (0)
+  if (a.pred_leaf) {
+    if (a.has_missing) QC_GO(true, true); else QC_GO(false, true);
+  } else {
+    if (a.has_missing) QC_GO(true, false); else QC_GO(false, false);
+  }
+#undef QC_GO
+  return QC_LAUNCHED();
+}
+
+cudaError_t launch_predict(const DeviceForest &f, const PredictArgs &a, const Tunables &t, cudaStream_t s) {
+  if (a.nrow == 0) return cudaSuccess;
+  int block = t.block > 0 ? t.block : 256;
+  if (block > 256) block = 256;
+  block = (block + 31) / 32 * 32;
+  switch (t.ilp > 0 ? t.ilp : 4) {
+    case 1: return launch_predict_ilp<1>(f, a, block, s);
+    case 2: return launch_predict_ilp<2>(f, a, block, s);
+    case 8: return launch_predict_ilp<8>(f, a, block, s);
+    default: return launch_predict_ilp<4>(f, a, block, s);
+  }
+}
+
+// =====================================================================================
+// K1 — Run1 feature assembly
+// =====================================================================================
+// oh_state: PL_MOD, NDWET (OH_GridCompMod.F90:1247-1257) and the level-slab count (:275-298).
+// One thread per column, coalesced across columns at every level.
+__global__ void __launch_bounds__(128) oh_state_kernel(Run1Dev r) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  int cnt = 0, bad = 0;
+  if (c < r.ncol) {
+    const float tropp = r.TROPP[c];
+    const float cmp = r.dynamic_k ? tropp : r.tropp_min;
+    if (!r.dynamic_k && tropp <= r.tropp_min) bad = 1;  // :287
+    float ple_up = r.PLE_MOD[c];
+    for (int k = 0; k < r.km; ++k) {
+      const size_t e = (size_t)k * r.ncol + c;
+      const float ple_dn = r.PLE_MOD[e + r.ncol];
+      const float pl = __fmul_rn(__fadd_rn(ple_up, ple_dn), 0.5f);  // :1247
+      const float q = r.Q_MOD[e];
+      // TV = T * (1 + Q/eps) / (1 + Q), left to right (:1250)
+      const float tv = __fdiv_rn(__fmul_rn(r.T_MOD[e], __fadd_rn(1.0f, __fdiv_rn(q, r.eps))), __fadd_rn(1.0f, q));
+      r.PL_MOD[e] = pl;
+      r.NDWET[e] = __fdiv_rn(__fmul_rn(r.avogad, pl), __fmul_rn(r.runiv, tv));  // :1257
+      cnt += pl > cmp;
+      ple_up = ple_dn;
+    }
+  }
+  cnt = __reduce_max_sync(0xffffffffu, cnt);
+  bad = __reduce_add_sync(0xffffffffu, bad);
+  if ((threadIdx.x & 31) == 0) {
+    atomicMax(&r.ctl[0], cnt);
+    if (bad) atomicAdd(&r.ctl[1], bad);
+  }
+}
+
+cudaError_t launch_oh_state(const Run1Dev &r, cudaStream_t s) {
+  oh_state_kernel<<<(r.ncol + 127) / 128, 128, 0, s>>>(r);
+  return QC_LAUNCHED();
+}
+
+// oh_sums: aod (:1451-1466) and the six vertical sums (:1468-1478).  Every SUM(x(:,:,a:b),3)
+// restarts at its first level and adds downward, so the DN sums are NOT a suffix scan: level k
+// needs its own forward chain x(k) + x(k+1) + ... (SURVEY.md hard part 6).  One thread per
+// column keeps KB chains per field in registers and sweeps the column once per block of KB
+// levels; the UP sums are a running prefix.  aod is kept in a scratch column (sums[5] is
+// reused as the aod buffer until the DN pass overwrites it level by level, top down, after
+// the level has been consumed by every chain that starts at or above it).
+constexpr int KB = 8;
+__global__ void __launch_bounds__(128) oh_sums_kernel(Run1Dev r, float *__restrict__ aod) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= r.ncol) return;
+  const int nc = r.ncol, km = r.km;
+  float *wdn = r.sums[0], *idn = r.sums[1], *iup = r.sums[2], *wup = r.sums[3], *aup = r.sums[4], *adn = r.sums[5];
+  // pass 1: aod and the UP prefixes
+  float s_iup = 0.f, s_wup = 0.f, s_aup = 0.f;
+  float z_up = r.ZLE_BST[c];
+  for (int k = 0; k < km; ++k) {
+    const size_t e = (size_t)k * nc + c;
+    const float z_dn = r.ZLE_BST[e + nc];
+    const float thick = __fadd_rn(z_up, -z_dn);  // REAL*8 gridBoxThickness holds this float exactly
+    float sc = __fadd_rn(r.SCA[0][e], r.SCA[1][e]);
+    sc = __fadd_rn(sc, r.SCA[2][e]);
+    sc = __fadd_rn(sc, r.SCA[3][e]);
+    sc = __fadd_rn(sc, r.SCA[4][e]);
+    sc = __fadd_rn(sc, r.SCA[5][e]);
+    sc = __fadd_rn(sc, r.SCA[6][e]);
+    // double(thick) * double(sc) is exact (24 + 24 bits), so rounding it to REAL equals the
+    // correctly rounded float32 product
+    const float a = __fmul_rn(thick, sc);
+    aod[e] = a;
+    s_iup = __fadd_rn(s_iup, r.TAUCLI[e]);
+    s_wup = __fadd_rn(s_wup, r.TAUCLW[e]);
+    s_aup = __fadd_rn(s_aup, a);
+    iup[e] = s_iup, wup[e] = s_wup, aup[e] = s_aup;
+    z_up = z_dn;
+  }
+  // pass 2: DN chains, KB start levels at a time
+  for (int k0 = 0; k0 < km; k0 += KB) {
+    float cw[KB], ci[KB], ca[KB];
+#pragma unroll
+    for (int j = 0; j < KB; ++j) cw[j] = ci[j] = ca[j] = 0.f;
+    for (int kk = k0; kk < km; ++kk) {
+      const size_t e = (size_t)kk * nc + c;
+      const float w = r.TAUCLW[e], i = r.TAUCLI[e], a = aod[e];
+#pragma unroll
+      for (int j = 0; j < KB; ++j)
+        if (k0 + j <= kk) {
+          cw[j] = __fadd_rn(cw[j], w);
+          ci[j] = __fadd_rn(ci[j], i);
+          ca[j] = __fadd_rn(ca[j], a);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < KB; ++j)
+      if (k0 + j < km) {
+        const size_t e = (size_t)(k0 + j) * nc + c;
+        wdn[e] = cw[j], idn[e] = ci[j], adn[e] = ca[j];
+      }
+  }
+}
+
+cudaError_t launch_oh_sums(const Run1Dev &r, cudaStream_t s) {
+  // aod scratch: OH_boost is not written until oh_finalize, borrow it
+  oh_sums_kernel<<<(r.ncol + 127) / 128, 128, 0, s>>>(r, r.OH_boost);
+  return QC_LAUNCHED();
+}
+
+// oh_pack: xx_carr(27, N) in the reference's order (OH_GridCompMod.F90:308-345): row m runs
+// over k = k1..km, then column (i fastest).  A CTA packs 256 consecutive rows: per feature the
+// 256 sources are contiguous (coalesced), the [256][27] tile is transposed through shared
+// memory (stride 27 is odd: conflict-free) and written back as one contiguous run.
+__global__ void __launch_bounds__(256) oh_pack_kernel(Run1Dev r, int k1, uint64_t npred, float *__restrict__ X) {
+  __shared__ float tile[256 * 27];
+  const int tid = threadIdx.x;
+  const uint64_t m0 = (uint64_t)blockIdx.x * 256;
+  const uint64_t m = m0 + tid;
+  int flags = 0;
+  if (m < npred) {
+    const size_t e = (size_t)(k1 - 1) * r.ncol + m;
+    const int c = (int)(m % (uint64_t)r.ncol);
+    float *row = tile + tid * 27;
+    row[0] = __fmul_rn(r.LATS[c], r.r2d);  // :1444
+    // PL_BST = (PLE(k-1) + PLE(k)) * 0.5 (:1488), then / 100.0 as a true divide (:314)
+    row[1] = __fdiv_rn(__fmul_rn(__fadd_rn(r.PLE_BST[e], r.PLE_BST[e + r.ncol]), 0.5f), 100.0f);
+    row[2] = r.T_BST[e];
+    row[3] = r.NO2[e];
+    row[4] = r.O3[e];
+    row[5] = r.CH4[e];
+    row[6] = r.CO[e];
+    row[7] = r.ISOP[e];
+    row[8] = r.ACET[e];
+    row[9] = r.C2H6[e];
+    row[10] = r.C3H8[e];
+    row[11] = r.PRPE[e];
+    row[12] = r.ALK4[e];
+    row[13] = r.MP[e];
+    row[14] = r.H2O2[e];
+    row[15] = r.sums[0][e];  // TAUCLWDN
+    row[16] = r.sums[1][e];  // TAUCLIDN
+    row[17] = r.sums[2][e];  // TAUCLIUP
+    row[18] = r.sums[3][e];  // TAUCLWUP
+    row[19] = r.FCLD[e];
+    row[20] = r.Q_BST[e];
+    row[21] = __fadd_rn(r.GMITO3[c], -r.GMITTO3[c]);  // :1446
+    row[22] = r.ALBUV[c];
+    row[23] = r.sums[4][e];  // AODUP
+    row[24] = r.sums[5][e];  // AODDN
+    row[25] = r.CH2O[e];
+    row[26] = r.SZA[c];
+    const bool fin = !isinf(r.missing);
+#pragma unroll
+    for (int f = 0; f < 27; ++f) {
+      const float v = row[f];
+      if (v != v || v == r.missing) flags |= 1;
+      if (fin && isinf(v)) flags |= 2;
+    }
+  }
+  flags = __reduce_or_sync(0xffffffffu, flags);
+  if ((tid & 31) == 0 && flags) atomicOr(&r.ctl[2], flags);
+  __syncthreads();
+  const uint64_t left = npred - m0;
+  const int n = (int)(left < 256 ? left : 256) * 27;
+  float *dst = X + m0 * 27;
+  for (int i = tid; i < n; i += 256) dst[i] = tile[i];
+}
+
+cudaError_t launch_oh_pack(const Run1Dev &r, int k1, float *X, cudaStream_t s) {
+  const uint64_t npred = (uint64_t)r.ncol * (uint64_t)(r.km - k1 + 1);
+  if (npred == 0) return cudaSuccess;
+  oh_pack_kernel<<<(unsigned)((npred + 255) / 256), 256, 0, s>>>(r, k1, npred, X);
+  return QC_LAUNCHED();
+}
+
+// oh_finalize (OH_GridCompMod.F90:1579-1599): OH_boost export, troposphere mask against the
+// climatological OH using the CURRENT model PL / TROPP, mol/mol -> molec/cm3.
+__global__ void __launch_bounds__(256) oh_finalize_kernel(Run1Dev r, uint64_t n) {
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += stride) {
+    const int c = (int)(e % (uint64_t)r.ncol);
+    const float ml = r.OH_ML[e];
+    if (r.OH_boost) r.OH_boost[e] = ml;
+    const float oh = (r.PL_MOD[e] > r.TROPP[c]) ? ml : r.OH_CLIM[e];
+    r.OH[e] = __fmul_rn(__fmul_rn(oh, r.NDWET[e]), 1.0e-6f);
+  }
+}
+
+cudaError_t launch_oh_finalize(const Run1Dev &r, cudaStream_t s) {
+  const uint64_t n = (uint64_t)r.ncol * r.km;
+  int blocks = (int)((n + 255) / 256 < 148 * 16 ? (n + 255) / 256 : 148 * 16);
+  oh_finalize_kernel<<<blocks, 256, 0, s>>>(r, n);
+  return QC_LAUNCHED();
+}
+
+// K4 — build-defined diagnostic (not in the reference): float64 partial sums
+//   [0] sum(OH * w)   [1] sum(w)            w = dP * area / g over tropospheric cells (PL > TROPP)
+//   [2] sum(nCH4 * V) [3] sum(k(T) * OH * nCH4 * V),  k = 2.45e-12 exp(-1775/T), V = area * dz
+// OH in molec/cm3, nCH4 = CH4 * NDWET.  The host (or NCCL) adds the ranks' partial sums.
+__global__ void __launch_bounds__(256) oh_diag_kernel(Run1Dev r, uint64_t n) {
+  double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += stride) {
+    const int c = (int)(e % (uint64_t)r.ncol);
+    if (r.PL_MOD[e] > r.TROPP[c]) {
+      const double area = r.AREA[c];
+      const double dp = (double)r.PLE_MOD[e + r.ncol] - (double)r.PLE_MOD[e];
+      const double dz = (double)r.ZLE_BST[e] - (double)r.ZLE_BST[e + r.ncol];
+      const double w = dp * area / 9.80665;
+      const double oh = r.OH[e];
+      const double nch4 = (double)r.CH4[e] * (double)r.NDWET[e];
+      const double kt = 2.45e-12 * exp(-1775.0 / (double)r.T_MOD[e]);
+      s0 += oh * w, s1 += w, s2 += nch4 * area * dz, s3 += kt * oh * nch4 * area * dz;
+    }
+  }
+  __shared__ double sh[4][8];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s0 += __shfl_down_sync(0xffffffffu, s0, o);
+    s1 += __shfl_down_sync(0xffffffffu, s1, o);
+    s2 += __shfl_down_sync(0xffffffffu, s2, o);
+    s3 += __shfl_down_sync(0xffffffffu, s3, o);
+  }
+  if (lane == 0) sh[0][wid] = s0, sh[1][wid] = s1, sh[2][wid] = s2, sh[3][wid] = s3;
+  __syncthreads();
+  if (threadIdx.x < 4) {
+    double t = 0;
+    for (int w = 0; w < 8; ++w) t += sh[threadIdx.x][w];
+    atomicAdd(&r.diag[threadIdx.x], t);
+  }
+}
+
+cudaError_t launch_oh_diag(const Run1Dev &r, cudaStream_t s) {
+  const uint64_t n = (uint64_t)r.ncol * r.km;
+  int blocks = (int)((n + 255) / 256 < 148 * 4 ? (n + 255) / 256 : 148 * 4);
+  oh_diag_kernel<<<blocks, 256, 0, s>>>(r, n);
+  return QC_LAUNCHED();
+}
+
+}  // namespace qcoh

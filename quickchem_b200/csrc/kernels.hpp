@@ -1,0 +1,81 @@
+// kernels.hpp — launch interface of the sm_100a kernels (kernels.cu), used by capi.cpp.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+namespace qcoh {
+
+// Device copy of a FlatForest (forest.hpp).
+struct DeviceForest {
+  const uint2 *nodes = nullptr;          // {value bits, meta}
+  const uint32_t *tree_offset = nullptr; // [ntree + 1]
+  const int32_t *tree_depth = nullptr;   // [ntree]
+  const int32_t *orig_id = nullptr;      // [num_nodes]
+  int32_t ntree = 0;
+  int32_t nfeat = 0;
+  int32_t max_depth = 0;
+  int64_t num_nodes = 0;
+  float base_score = 0.f;
+};
+
+struct PredictArgs {
+  const float *X = nullptr;  // [nrow][ncol] row-major, device
+  uint64_t nrow = 0;
+  int32_t ncol = 0;
+  float missing = 0.f;
+  int has_missing = 1;       // 0: the sealed matrix holds no NaN / == missing entry
+  int pred_leaf = 0;         // option_mask & 2
+  int32_t ntree_used = 0;
+  int exp10 = 0;             // fused export transform, OH_GridCompMod.F90:369,1569
+  float scale = 1.f;
+  float *out = nullptr;      // device: [nrow] or [nrow][ntree_used]
+};
+
+struct Tunables {
+  int variant = 0;   // 0 = default
+  int ilp = 0;       // trees walked concurrently per thread (0 = default)
+  int block = 0;     // threads per CTA (0 = default)
+  int top_levels = 0;
+};
+
+uint64_t launch_count();
+
+// flags[0] |= 1 if any entry is NaN or == missing; flags[0] |= 2 if any entry is +-inf
+// (and `missing` is finite) — what XGDMatrixCreateFromMat checks (xgboost src/data/data.cc).
+cudaError_t launch_scan_matrix(const float *X, uint64_t n, float missing, int *flags, cudaStream_t s);
+
+cudaError_t launch_predict(const DeviceForest &f, const PredictArgs &a, const Tunables &t, cudaStream_t s);
+
+// ---- fused Run1 pieces (OH_GridCompMod.F90:1232-1599) ---------------------------------
+struct Run1Dev {
+  int32_t ncol = 0, km = 0;
+  float eps = 0, avogad = 0, runiv = 0, r2d = 0;
+  float ohscale = 1.f, tropp_min = 4000.f, missing = -999.f;
+  int dynamic_k = 0;
+  const float *T_MOD, *Q_MOD, *PLE_MOD, *TROPP;
+  const float *T_BST, *Q_BST, *PLE_BST, *ZLE_BST;
+  const float *TAUCLW, *TAUCLI, *FCLD, *CH4, *CO;
+  const float *SCA[7];
+  const float *NO2, *O3, *ISOP, *ACET, *C2H6, *C3H8, *PRPE, *ALK4, *MP, *H2O2, *CH2O;
+  const float *GMITO3, *GMITTO3, *ALBUV, *LATS;
+  const float *SZA;      // [ncol] degrees (host-computed with libm, see oh_host.cpp)
+  const float *OH_CLIM;
+  const float *AREA;
+  // work / outputs (device)
+  float *PL_MOD, *NDWET;             // [km][ncol]
+  float *sums[6];                    // wdn idn iup wup aup adn, [km][ncol]
+  float *OH_ML;                      // persistent [km][ncol]
+  float *OH, *OH_boost;              // [km][ncol]
+  int *ctl;                          // [0] ksub (atomicMax) [1] tropp<=tropp_min count [2] matrix flags
+  double *diag;                      // [4]
+};
+
+cudaError_t launch_oh_state(const Run1Dev &r, cudaStream_t s);
+cudaError_t launch_oh_sums(const Run1Dev &r, cudaStream_t s);
+cudaError_t launch_oh_pack(const Run1Dev &r, int k1, float *X, cudaStream_t s);
+cudaError_t launch_oh_finalize(const Run1Dev &r, cudaStream_t s);
+cudaError_t launch_oh_diag(const Run1Dev &r, cudaStream_t s);
+cudaError_t launch_fill(float *p, uint64_t n, float v, cudaStream_t s);
+
+}  // namespace qcoh

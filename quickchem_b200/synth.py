@@ -79,14 +79,21 @@ def _ar1(rng, shape, rho=0.95, nrow_len=None) -> np.ndarray:
     return out.reshape(shape)
 
 
-def raw_fields(n: int, seed: int | None = None, km: int = KM, rho: float = 0.95) -> Dict[str, np.ndarray]:
+def raw_fields(n: int, seed: int | None = None, km: int = KM, rho: float = 0.95, col0: int = 0,
+               ncol: int | None = None) -> Dict[str, np.ndarray]:
     """Synthetic import state for `OH_data_source = ONLINE_INST` on cubed sphere C<n>.
 
     Distributions follow SURVEY.md §8(d).  `rho=0` gives the uncorrelated worst case.
+    `col0`/`ncol` restrict the state to one rank's contiguous column range (a multiple of `n`
+    columns, i.e. whole j-rows, so the AR(1) rows stay intact); seed it per rank.
     """
     rng = np.random.default_rng(20220726 + n if seed is None else seed)
-    _, _, ncol = grid_dims(n)
     lat, lon = cubed_sphere_latlon(n)
+    if ncol is None:
+        _, _, ncol = grid_dims(n)
+        ncol -= col0
+    assert ncol % n == 0 and col0 % n == 0, "shards are whole j-rows of the (N, 6N) index space"
+    lat, lon = lat[col0 : col0 + ncol], lon[col0 : col0 + ncol]
     f: Dict[str, np.ndarray] = {"LATS": lat, "LONS": lon}
 
     def noise3(sig_col=0.6, sig_cell=0.8):

@@ -1,0 +1,169 @@
+"""GPU parity of the fused Run1 path (qcoh_oh_run1) and of the host mirror of
+`predict_OH_with_XGB` against the oracle's Run1 restatement (OH_GridCompMod.F90:1232-1599).
+
+Bars: the assembled feature matrix X (all 27 features, incl. the O(km^2) restarted vertical sums
+and the host-libm noon SZA), the level slab k1, and the raw booster output are bit-exact; OH,
+OH_boost within 1e-6 relative (10**x: float64 exp10 on device vs libm powf); NDWET bit-exact."""
+import numpy as np
+import pytest
+
+from quickchem_b200 import synth
+
+pytestmark = pytest.mark.gpu
+REL_TOL_OH = 1e-6
+
+
+def _rel(a, b):
+    a, b = a.astype(np.float64), b.astype(np.float64)
+    d = np.abs(a - b)
+    return float(np.max(np.where(d == 0, 0.0, d / np.maximum(np.abs(b), 1e-300))))
+
+
+def _run_both(capi, oracle, model_path, fields, **kw):
+    km, ncol = fields["T"].shape
+    b = capi.Booster(model_path)
+    oh = capi.OhRun1(b, ncol, km, synth.MAPL, ohscale=kw.get("ohscale", 0.85),
+                     compute_once_per_day=kw.get("compute_once_per_day", True))  # fmt: skip
+    rin = oh.make_in(fields, nymd=kw.get("nymd", 20220701), mod_fields=kw.get("mod_fields"))
+    got = oh.run(rin, want=("OH", "OH_boost", "NDWET", "X", "pred"))
+    ref = oracle.run1(oracle.Model(model_path), fields, synth.MAPL, ohscale=kw.get("ohscale", 0.85),
+                      compute_once_per_day=kw.get("compute_once_per_day", True), nymd=kw.get("nymd", 20220701),
+                      mod_fields=kw.get("mod_fields"), want_features=True)  # fmt: skip
+    return got, ref, oh, rin
+
+
+def _assert_parity(got, ref):
+    assert got["k1"] == ref["k1"]
+    assert got["X"].shape == ref["X"].shape
+    for f in range(27):
+        assert np.array_equal(got["X"][:, f].view(np.uint32), ref["X"][:, f].view(np.uint32)), synth.FEATURE_NAMES[f]
+    assert np.array_equal(got["pred"].view(np.uint32), ref["pred"].view(np.uint32))
+    assert np.array_equal(got["NDWET"].view(np.uint32), ref["NDWET"].view(np.uint32))
+    assert _rel(got["OH_boost"], ref["OH_boost"]) <= REL_TOL_OH
+    assert _rel(got["OH"], ref["OH"]) <= REL_TOL_OH
+
+
+@pytest.mark.parametrize("n", [6, 24])
+def test_run1_once_per_day(capi, oracle, small_model_path, n):
+    """configs[0]: C24 x 72 single-timestep OH prediction (and a smaller grid)."""
+    fields = synth.raw_fields(n)
+    got, ref, _, _ = _run_both(capi, oracle, small_model_path, fields)
+    assert 1 < got["k1"] < 72  # the 40 hPa slab, not all levels
+    _assert_parity(got, ref)
+    # levels above the slab are zero in OH_boost (self%OH_ML = 0.0, :1559)
+    assert np.all(got["OH_boost"][: got["k1"] - 1] == 0)
+
+
+def test_run1_dynamic_k_range(capi, oracle, small_model_path):
+    fields = synth.raw_fields(8)
+    got, ref, _, _ = _run_both(capi, oracle, small_model_path, fields, compute_once_per_day=False, nymd=20240229)
+    _assert_parity(got, ref)
+
+
+def test_run1_distinct_model_state(capi, oracle, small_model_path):
+    """ONLINE_AVG24 / PRECOMPUTED: model-state T/Q/PLE differ from the boost-state ones."""
+    fields = synth.raw_fields(8)
+    mod = synth.raw_fields(8, seed=99)
+    got, ref, _, _ = _run_both(capi, oracle, small_model_path, fields, mod_fields=mod)
+    _assert_parity(got, ref)
+
+
+def test_run1_tropopause_assert(capi, oracle, small_model_path):
+    fields = dict(synth.raw_fields(4))
+    fields["TROPP"] = fields["TROPP"].copy()
+    fields["TROPP"][5] = 3999.0
+    b = capi.Booster(small_model_path)
+    oh = capi.OhRun1(b, fields["T"].shape[1], 72, synth.MAPL)
+    with pytest.raises(capi.QcohError, match="tropopause"):
+        oh.run(oh.make_in(fields))
+    with pytest.raises(oracle.OracleError, match="tropopause"):
+        oracle.run1(oracle.Model(small_model_path), fields, synth.MAPL)
+
+
+def test_run1_persistent_oh_ml_and_device_fields(capi, oracle, small_model_path):
+    """configs[4] semantics: fields resident in HBM, boost once, later steps reuse OH_ML while
+    PL / TROPP / NDWET follow the current model state (OH_GridCompMod.F90:1189-1193,1579-1595)."""
+    fields = synth.raw_fields(8)
+    km, ncol = fields["T"].shape
+    dev = {k: capi.DeviceArray(v) for k, v in fields.items()}
+    b = capi.Booster(small_model_path)
+    oh = capi.OhRun1(b, ncol, km, synth.MAPL)
+    first = oh.run(oh.make_in(dev, need_to_call_boost=True))
+    ref = oracle.run1(oracle.Model(small_model_path), fields, synth.MAPL)
+    assert _rel(first["OH"], ref["OH"]) <= REL_TOL_OH
+    # an hour later: new model state, boost skipped
+    later = synth.raw_fields(8, seed=4242)
+    step2 = dict(dev)
+    for k in ("T", "Q", "PLE", "TROPP"):
+        step2[k] = capi.DeviceArray(later[k])
+    got = oh.run(oh.make_in(fields=dev, mod_fields=step2, need_to_call_boost=False))
+    # expected: same OH_ML, masked / converted with the new state
+    pl = (later["PLE"][:-1] + later["PLE"][1:]) * np.float32(0.5)
+    tv = later["T"] * (np.float32(1.0) + later["Q"] / synth.MAPL["EPSILON"]) / (np.float32(1.0) + later["Q"])
+    ndwet = (synth.MAPL["AVOGAD"] * pl) / (synth.MAPL["RUNIV"] * tv)
+    oh_sel = np.where(pl > later["TROPP"][None, :], first["OH_boost"], fields["oh_OH"])
+    expect = (oh_sel * ndwet) * np.float32(1.0e-6)
+    assert np.array_equal(got["OH"].view(np.uint32), expect.astype(np.float32).view(np.uint32))
+
+
+def test_run1_needs_a_boost_call_first(capi, small_model_path):
+    fields = synth.raw_fields(4)
+    oh = capi.OhRun1(capi.Booster(small_model_path), fields["T"].shape[1], 72, synth.MAPL)
+    with pytest.raises(capi.QcohError, match="need_to_call_boost"):
+        oh.run(oh.make_in(fields, need_to_call_boost=False))
+
+
+def test_diag_partial_sums(capi, small_model_path):
+    """Build-defined diagnostic (not in the reference): float64 numpy is the oracle, 1e-10 rel."""
+    fields = synth.raw_fields(8)
+    km, ncol = fields["T"].shape
+    area = (np.random.default_rng(1).random(ncol) * 1e9 + 1e9).astype(np.float32)
+    oh = capi.OhRun1(capi.Booster(small_model_path), ncol, km, synth.MAPL)
+    got = oh.run(oh.make_in(fields, area=area), want=("OH", "NDWET"))
+    f64 = lambda a: a.astype(np.float64)
+    pl = (fields["PLE"][:-1] + fields["PLE"][1:]) * np.float32(0.5)
+    trop = pl > fields["TROPP"][None, :]
+    dp = f64(fields["PLE"][1:]) - f64(fields["PLE"][:-1])
+    dz = f64(fields["ZLE"][:-1]) - f64(fields["ZLE"][1:])
+    w = dp * f64(area)[None, :] / 9.80665
+    nch4 = f64(fields["CH4"]) * f64(got["NDWET"])
+    kt = 2.45e-12 * np.exp(-1775.0 / f64(fields["T"]))
+    vol = f64(area)[None, :] * dz
+    expect = np.array([(f64(got["OH"]) * w)[trop].sum(), w[trop].sum(), (nch4 * vol)[trop].sum(),
+                       (kt * f64(got["OH"]) * nch4 * vol)[trop].sum()])  # fmt: skip
+    assert np.allclose(got["diag"], expect, rtol=1e-10, atol=0)
+
+
+def test_host_mirror_predict_OH_with_XGB(capi, oracle, small_model_path):
+    """The reference's own driver routine, restated on the host and linked against libqcoh's
+    XGBoost-named symbols only, against the oracle's Run1 (same inputs)."""
+    fields = synth.raw_fields(6)
+    km, ncol = fields["T"].shape
+    ref = oracle.run1(oracle.Model(small_model_path), fields, synth.MAPL, ohscale=1.0, want_features=True)
+    # bb from the oracle-assembled features (feature 2 is PL in Pa before the /100 of :314)
+    k1 = ref["k1"]
+    pl_mod = ((fields["PLE"][:-1] + fields["PLE"][1:]) * np.float32(0.5)).astype(np.float32)
+    X = np.zeros((km * ncol, 27), np.float32)
+    X[(k1 - 1) * ncol :] = ref["X"]
+    bb = []
+    for f in range(27):
+        if f in (0, 21, 22, 26):
+            bb.append(np.ascontiguousarray(ref["X"][:ncol, f]))
+        elif f == 1:
+            bb.append(pl_mod)
+        else:
+            bb.append(np.ascontiguousarray(X[:, f].reshape(km, ncol)))
+    capi.lib().qcoh_predict_OH_reset()
+    OH_ML = np.zeros((km, ncol), np.float32)
+    rc = capi.predict_OH_with_XGB(small_model_path, 6, ncol // 6, km, False, 4000.0, pl_mod, fields["TROPP"], bb, OH_ML)
+    assert rc == 0, capi.last_error()
+    # dynamic_k_range=False => same 40 hPa slab as the oracle's compute_once_per_day run
+    assert np.all(OH_ML[: k1 - 1] == 0)
+    expect = np.float32(10.0) ** ref["pred"].reshape(km - k1 + 1, ncol)
+    assert _rel(OH_ML[k1 - 1 :], expect.astype(np.float32)) <= REL_TOL_OH
+    # second call reuses the SAVEd booster (first_time = .FALSE.)
+    OH2 = np.zeros_like(OH_ML)
+    assert capi.predict_OH_with_XGB("/nonexistent/ignored.model", 6, ncol // 6, km, False, 4000.0, pl_mod,
+                                    fields["TROPP"], bb, OH2) == 0  # fmt: skip
+    assert np.array_equal(OH_ML, OH2)
+    capi.lib().qcoh_predict_OH_reset()
