@@ -80,14 +80,17 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
+        """Summarise the samples taken inside [t0, t1] (the timed region)."""
         if self.proc:
+            time.sleep(0.15)
             self.proc.terminate()
         sm, reasons, smax = [], set(), None
         names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
-        for r in self.rows:
+        inside = [r for ts, r in self.rows if (t0 is None or ts >= t0) and (t1 is None or ts <= t1 + 0.1)]
+        for r in inside or [r for _, r in self.rows[-3:]]:
             try:
                 sm.append(float(r[0]))
                 smax = float(r[1])
@@ -168,7 +171,7 @@ def workload_config(grid, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="qcoh", choices=["qcoh", "reference"])
     ap.add_argument("--grid", type=int, default=360, help="cubed-sphere C<grid> (BASELINE configs[2] = 360)")
@@ -241,15 +244,19 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    window = [0.0, 0.0]
+
     def timed(fn, steps, warm):
         for _ in range(warm):
             fn()
         barrier()
         n0 = capi.launch_count()
+        window[0] = time.time()
         capi.timer_start()
         for _ in range(steps):
             fn()
         ms = capi.timer_stop()
+        window[1] = time.time()
         barrier()
         return max_over_ranks(ms) / steps, capi.launch_count() - n0
 
@@ -257,11 +264,12 @@ def main():
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+        time.sleep(0.5)  # let nvidia-smi start sampling before the warm-up
 
     # ---- value: predict step on the resident matrix (K2 + fused export transform)
     step = lambda: booster.predict_device(dX, d_pred, exp10=True, scale=0.85)
     ms_step, launches = timed(step, args.steps, args.warmup)
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(*window) if rank == 0 else None
     value = total_cells / (ms_step * 1e-3)
 
     # ---- run1: fused device-resident Run1 (+ NCCL all-reduce of the diagnostic at N > 1)
@@ -351,7 +359,6 @@ def main():
         pass
     peak = peaks.get("hbm_gbs", 6650.0)
     achieved = (ncell * ALGO_BYTES_PER_CELL / 1e9) / (ms_step * 1e-3)  # per GPU: this rank's launch
-    visits = None
     out = {
         "metric": "OH grid-cell predictions/sec", "value": value, "unit": "cells/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,

@@ -44,7 +44,7 @@ struct HostForest {
 constexpr uint32_t kMetaFeatShift = 24;
 constexpr uint32_t kMetaDefaultLeftBit = 1u << 23;
 constexpr uint32_t kMetaRelMask = (1u << 23) - 1;
-constexpr uint32_t kMaxFeatures = 254;
+constexpr uint32_t kMaxFeatures = 31;  // the predict kernel stages a row through 32 registers
 
 struct FlatForest {
   std::vector<uint32_t> nodes_xy;     // 2 words per node

@@ -63,19 +63,19 @@ cudaError_t launch_fill(float *p, uint64_t n, float v, cudaStream_t s) {
 // =====================================================================================
 // K2 — predict
 // =====================================================================================
-// One thread = one row (grid cell).  The CTA's rows are staged in shared memory as
-// srow[row][S] with S odd (bank = (row*S + f) mod 32 is a bijection over a warp's 32 rows, so
-// the data-dependent feature fetch never bank-conflicts).  Slot `nfeat` of every row holds
-// -inf: leaves are encoded with feat = nfeat and rel = 0, so `!(v < x)` is false there and the
-// walk self-loops — the descent is a fixed-trip-count loop with no leaf test and no divergent
-// branch.  Missing entries (NaN or == missing) are canonicalised to NaN while staging.
+// One thread = one row (grid cell).  The CTA's rows are staged in shared memory TRANSPOSED,
+// srow[f][tid]: whatever feature each lane asks for, lane L always hits bank L — the
+// data-dependent feature fetch is bank-conflict-free by construction.  Slot `nfeat` of every row
+// holds -inf: leaves are encoded with feat = nfeat and rel = 0, so `!(v < x)` is false there and
+// the walk self-loops — the descent is a fixed-trip-count loop with no leaf test and no
+// divergent branch.  Missing entries (NaN or == missing) are canonicalised to NaN while staging.
 //
 // XGBoost semantics restated (xgboost 1.6.0 src/predictor/predict_fn.h GetNextNode,
 // src/predictor/cpu_predictor.cc PredictByAllTrees): missing -> default child, else
 // left + !(fvalue < split_cond); out = base_score, then += leaf value tree by tree in float32.
 template <int ILP, bool HAS_MISSING>
 __device__ __forceinline__ void walk_group(const uint2 *__restrict__ nodes, const uint32_t *__restrict__ toff,
-                                           const int32_t *__restrict__ tdepth, int t, const float *my,
+                                           const int32_t *__restrict__ tdepth, int t, const float *my, int fstride,
                                            uint32_t (&idx)[ILP], uint32_t (&xbits)[ILP]) {
   int depth = 0;
 #pragma unroll
@@ -89,7 +89,7 @@ __device__ __forceinline__ void walk_group(const uint2 *__restrict__ nodes, cons
 #pragma unroll
     for (int j = 0; j < ILP; ++j) {
       const uint2 nd = __ldg(nodes + idx[j]);
-      const float v = my[nd.y >> kMetaFeatShift];
+      const float v = my[(nd.y >> kMetaFeatShift) * fstride];
       bool right = !(v < __uint_as_float(nd.x));
       if (HAS_MISSING) {
         if (v != v) right = !(nd.y & kMetaDefaultLeftBit);
@@ -108,71 +108,93 @@ __device__ __forceinline__ float export_transform(float acc, int exp10_on, float
   return __fmul_rn(p, scale);
 }
 
-template <int ILP, bool HAS_MISSING, bool PRED_LEAF>
-__global__ void __launch_bounds__(256) predict_rows_kernel(DeviceForest f, PredictArgs a, int S) {
+// LOCKSTEP: one 1024-thread CTA per SM walks tree t with all its warps before any warp starts
+// tree t + 1 (a barrier per tree group), so the SM's L1 only has to hold the tree being walked.
+template <int ILP, bool HAS_MISSING, bool PRED_LEAF, bool LOCKSTEP, int MAXT>
+__global__ void __launch_bounds__(MAXT) predict_rows_kernel(DeviceForest f, PredictArgs a) {
   extern __shared__ float srow[];
   const int tid = threadIdx.x;
-  const uint64_t r0 = (uint64_t)blockIdx.x * blockDim.x;
+  const int B = blockDim.x;
+  const uint64_t r0 = (uint64_t)blockIdx.x * B;
   const uint64_t left = a.nrow - r0;
-  const int nr = left < (uint64_t)blockDim.x ? (int)left : (int)blockDim.x;
+  const int nr = left < (uint64_t)B ? (int)left : B;
   const int ncol = a.ncol;
   {
+    // stage 1: coalesced copy of the tile's rows, row-major (the tile is one contiguous run of X)
     const float *__restrict__ src = a.X + r0 * (uint64_t)ncol;
     const int n = nr * ncol;
+    for (int i = tid; i < n; i += B) srow[i] = __ldg(src + i);
+    __syncthreads();
+    // stage 2: each thread lifts its own row into registers (stride ncol: conflict-free for the
+    // 27-column matrix), then writes it back transposed
     const float qnan = __int_as_float(0x7fc00000);
-    for (int i = tid; i < n; i += blockDim.x) {
-      const int row = i / ncol;
-      const int col = i - row * ncol;
-      float v = __ldg(src + i);
-      if (HAS_MISSING && v == a.missing) v = qnan;
-      srow[row * S + col] = v;
-    }
+    float v[32];
+    const int nc32 = ncol < 32 ? ncol : 32;
+#pragma unroll
+    for (int c = 0; c < 32; ++c) v[c] = (c < nc32 && tid < nr) ? srow[tid * ncol + c] : 0.f;
+    __syncthreads();
+#pragma unroll
+    for (int c = 0; c < 32; ++c)
+      if (c < nc32) {
+        float x = v[c];
+        if (HAS_MISSING && x == a.missing) x = qnan;
+        srow[c * B + tid] = x;
+      }
     // columns the matrix does not have are missing (xgboost FVec::Fill leaves them flagged)
-    for (int c = ncol; c < f.nfeat; ++c) srow[tid * S + c] = qnan;
-    srow[tid * S + f.nfeat] = -INFINITY;
+    for (int c = nc32; c < f.nfeat; ++c) srow[c * B + tid] = qnan;
+    srow[f.nfeat * B + tid] = -INFINITY;
   }
-  __syncthreads();
-  if (tid >= nr) return;
-  const float *my = srow + tid * S;
+  if (!LOCKSTEP && tid >= nr) return;
+  const bool live = tid < nr;
+  const float *my = srow + tid;
   const uint64_t row = r0 + tid;
   const int ntree = a.ntree_used;
   float acc = f.base_score;
   int t = 0;
   for (; t + ILP <= ntree; t += ILP) {
     uint32_t idx[ILP], xb[ILP];
-    walk_group<ILP, HAS_MISSING>(f.nodes, f.tree_offset, f.tree_depth, t, my, idx, xb);
+    if (LOCKSTEP) __syncthreads();
+    walk_group<ILP, HAS_MISSING>(f.nodes, f.tree_offset, f.tree_depth, t, my, B, idx, xb);
 #pragma unroll
     for (int j = 0; j < ILP; ++j) {
-      if (PRED_LEAF)
-        a.out[row * (uint64_t)ntree + t + j] = (float)__ldg(f.orig_id + idx[j]);
-      else
+      if (PRED_LEAF) {
+        if (live) a.out[row * (uint64_t)ntree + t + j] = (float)__ldg(f.orig_id + idx[j]);
+      } else {
         acc = __fadd_rn(acc, __uint_as_float(xb[j]));
+      }
     }
   }
   for (; t < ntree; ++t) {
     uint32_t idx[1], xb[1];
-    walk_group<1, HAS_MISSING>(f.nodes, f.tree_offset, f.tree_depth, t, my, idx, xb);
-    if (PRED_LEAF)
-      a.out[row * (uint64_t)ntree + t] = (float)__ldg(f.orig_id + idx[0]);
-    else
+    walk_group<1, HAS_MISSING>(f.nodes, f.tree_offset, f.tree_depth, t, my, B, idx, xb);
+    if (PRED_LEAF) {
+      if (live) a.out[row * (uint64_t)ntree + t] = (float)__ldg(f.orig_id + idx[0]);
+    } else {
       acc = __fadd_rn(acc, __uint_as_float(xb[0]));
+    }
   }
-  if (!PRED_LEAF) a.out[row] = export_transform(acc, a.exp10, a.scale);
+  if (!PRED_LEAF && live) a.out[row] = export_transform(acc, a.exp10, a.scale);
 }
 
-template <int ILP>
+template <int ILP, bool LOCKSTEP, int MAXT>
 static cudaError_t launch_predict_ilp(const DeviceForest &f, const PredictArgs &a, int block, cudaStream_t s) {
-  const int S = (f.nfeat + 1) | 1;
-  const size_t smem = (size_t)block * S * sizeof(float);
+  // srow holds max(ncol, nfeat + 1) feature slots per thread
+  const int slots = (f.nfeat + 1) > a.ncol ? (f.nfeat + 1) : a.ncol;
+  size_t smem = (size_t)block * slots * sizeof(float);
+  if (LOCKSTEP && smem < (size_t)116 * 1024) smem = (size_t)116 * 1024;  // > half an SM: one CTA per SM
   const uint64_t nblk = (a.nrow + block - 1) / block;
   if (nblk > 0x7fffffffull) return cudaErrorInvalidConfiguration;
   const dim3 grid((unsigned)nblk);
 #define QC_GO(HM, PL)                                                                                            \
   do {                                                                                                           \
-    auto k = predict_rows_kernel<ILP, HM, PL>;                                                                   \
+    auto k = predict_rows_kernel<ILP, HM, PL, LOCKSTEP, MAXT>;                                                   \
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);             \
     if (e != cudaSuccess) return e;                                                                              \
-    k<<<grid, block, smem, s>>>(f, a, S);                                                                        \
+    if (LOCKSTEP) {                                                                                              \
+      e = cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, 51);                           \
+      if (e != cudaSuccess) return e;                                                                            \
+    }                                                                                                            \
+    k<<<grid, block, smem, s>>>(f, a);                                                                           \
   } while (0)
   if (a.pred_leaf) {
     if (a.has_missing) QC_GO(true, true); else QC_GO(false, true);
@@ -185,14 +207,23 @@ static cudaError_t launch_predict_ilp(const DeviceForest &f, const PredictArgs &
 
 cudaError_t launch_predict(const DeviceForest &f, const PredictArgs &a, const Tunables &t, cudaStream_t s) {
   if (a.nrow == 0) return cudaSuccess;
+  if (a.ncol > 32 || f.nfeat > 31) return cudaErrorInvalidValue;  // staged through 32 registers; capi.cpp reports it
+  if (t.variant == 1) {
+    int block = t.block > 0 ? (t.block + 31) / 32 * 32 : 1024;
+    if (block > 1024) block = 1024;
+    switch (t.ilp > 0 ? t.ilp : 1) {
+      case 2: return launch_predict_ilp<2, true, 1024>(f, a, block, s);
+      default: return launch_predict_ilp<1, true, 1024>(f, a, block, s);
+    }
+  }
   int block = t.block > 0 ? t.block : 256;
   if (block > 256) block = 256;
   block = (block + 31) / 32 * 32;
-  switch (t.ilp > 0 ? t.ilp : 4) {
-    case 1: return launch_predict_ilp<1>(f, a, block, s);
-    case 2: return launch_predict_ilp<2>(f, a, block, s);
-    case 8: return launch_predict_ilp<8>(f, a, block, s);
-    default: return launch_predict_ilp<4>(f, a, block, s);
+  switch (t.ilp > 0 ? t.ilp : 2) {
+    case 1: return launch_predict_ilp<1, false, 256>(f, a, block, s);
+    case 4: return launch_predict_ilp<4, false, 256>(f, a, block, s);
+    case 8: return launch_predict_ilp<8, false, 256>(f, a, block, s);
+    default: return launch_predict_ilp<2, false, 256>(f, a, block, s);
   }
 }
 
