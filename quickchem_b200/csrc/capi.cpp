@@ -164,6 +164,11 @@ struct DMatrix {
   bool sealed = false;
 };
 
+// XGDMatrixFree keeps the largest freed matrix buffer for the next XGDMatrixCreateFromMat: the
+// reference creates and frees a same-sized DMatrix on every call (OH_GridCompMod.F90:347,377) and
+// cudaMalloc / cudaFree of multi-GB buffers would otherwise dominate the step.
+DevBuf<float> g_spare_X;
+
 Booster *B(BoosterHandle h) {
   Booster *b = (Booster *)h;
   if (!b || b->magic != kBoosterMagic) throw Error("Invalid booster handle");
@@ -290,6 +295,7 @@ int XGDMatrixCreateFromMat(const float *data, bst_ulong nrow, bst_ulong ncol, fl
   std::unique_ptr<DMatrix> d(new DMatrix());
   d->nrow = nrow, d->ncol = ncol, d->missing = missing;
   const size_t n = (size_t)nrow * ncol;
+  if (g_spare_X.cap >= n && g_spare_X.p) std::swap(d->X, g_spare_X);
   d->X.need(n);
   if (n) {
     // borrowed for this call only (the reference deallocates xx_carr right after predict,
@@ -306,6 +312,7 @@ int XGDMatrixFree(DMatrixHandle handle) {
   API_BEGIN
   DMatrix *d = D(handle);
   d->magic = 0;
+  if (d->X.cap > g_spare_X.cap) std::swap(d->X, g_spare_X);
   delete d;
   API_END
 }
@@ -487,6 +494,7 @@ int qcoh_set_param(const char *name, const char *value) {
   else if (n == "ilp") g.tun.ilp = v;
   else if (n == "block") g.tun.block = v;
   else if (n == "top_levels") g.tun.top_levels = v;
+  else if (n == "park") g.tun.park = v;
   else throw Error("qcoh_set_param: unknown parameter '" + n + "'");
   API_END
 }

@@ -73,7 +73,7 @@ cudaError_t launch_fill(float *p, uint64_t n, float v, cudaStream_t s) {
 // XGBoost semantics restated (xgboost 1.6.0 src/predictor/predict_fn.h GetNextNode,
 // src/predictor/cpu_predictor.cc PredictByAllTrees): missing -> default child, else
 // left + !(fvalue < split_cond); out = base_score, then += leaf value tree by tree in float32.
-template <int ILP, bool HAS_MISSING>
+template <int ILP, bool HAS_MISSING, bool PARK>
 __device__ __forceinline__ void walk_group(const uint2 *__restrict__ nodes, const uint32_t *__restrict__ toff,
                                            const int32_t *__restrict__ tdepth, int t, const float *my, int fstride,
                                            uint32_t (&idx)[ILP], uint32_t (&xbits)[ILP]) {
@@ -83,6 +83,32 @@ __device__ __forceinline__ void walk_group(const uint2 *__restrict__ nodes, cons
     idx[j] = __ldg(toff + t + j);
     depth = max(depth, __ldg(tdepth + t + j));
     xbits[j] = 0;
+  }
+  if (PARK) {
+    // Lanes that have reached their leaf stop fetching: a parked lane would otherwise re-read its
+    // own leaf sector on every remaining level, and at the deep levels those are 32 different
+    // sectors per warp request — the L1TEX data stage is the bound of this kernel.
+    bool done[ILP];
+#pragma unroll
+    for (int j = 0; j < ILP; ++j) done[j] = false;
+    for (int d = 0; d <= depth; ++d) {
+#pragma unroll
+      for (int j = 0; j < ILP; ++j) {
+        if (!done[j]) {
+          const uint2 nd = __ldg(nodes + idx[j]);
+          const float v = my[(nd.y >> kMetaFeatShift) * fstride];
+          bool right = !(v < __uint_as_float(nd.x));
+          if (HAS_MISSING) {
+            if (v != v) right = !(nd.y & kMetaDefaultLeftBit);
+          }
+          const uint32_t rel = nd.y & kMetaRelMask;
+          idx[j] += rel + (right ? 1u : 0u);
+          xbits[j] = nd.x;
+          done[j] = rel == 0;
+        }
+      }
+    }
+    return;
   }
   // depth + 1 fetches: the last one reads the leaf itself, whose x word is the leaf value
   for (int d = 0; d <= depth; ++d) {
@@ -108,10 +134,8 @@ __device__ __forceinline__ float export_transform(float acc, int exp10_on, float
   return __fmul_rn(p, scale);
 }
 
-// LOCKSTEP: one 1024-thread CTA per SM walks tree t with all its warps before any warp starts
-// tree t + 1 (a barrier per tree group), so the SM's L1 only has to hold the tree being walked.
-template <int ILP, bool HAS_MISSING, bool PRED_LEAF, bool LOCKSTEP, int MAXT>
-__global__ void __launch_bounds__(MAXT) predict_rows_kernel(DeviceForest f, PredictArgs a) {
+template <int ILP, bool HAS_MISSING, bool PRED_LEAF, bool PARK>
+__global__ void __launch_bounds__(256, 6) predict_rows_kernel(DeviceForest f, PredictArgs a) {
   extern __shared__ float srow[];
   const int tid = threadIdx.x;
   const int B = blockDim.x;
@@ -144,8 +168,8 @@ __global__ void __launch_bounds__(MAXT) predict_rows_kernel(DeviceForest f, Pred
     for (int c = nc32; c < f.nfeat; ++c) srow[c * B + tid] = qnan;
     srow[f.nfeat * B + tid] = -INFINITY;
   }
-  if (!LOCKSTEP && tid >= nr) return;
-  const bool live = tid < nr;
+  if (tid >= nr) return;
+  const bool live = true;
   const float *my = srow + tid;
   const uint64_t row = r0 + tid;
   const int ntree = a.ntree_used;
@@ -153,8 +177,7 @@ __global__ void __launch_bounds__(MAXT) predict_rows_kernel(DeviceForest f, Pred
   int t = 0;
   for (; t + ILP <= ntree; t += ILP) {
     uint32_t idx[ILP], xb[ILP];
-    if (LOCKSTEP) __syncthreads();
-    walk_group<ILP, HAS_MISSING>(f.nodes, f.tree_offset, f.tree_depth, t, my, B, idx, xb);
+    walk_group<ILP, HAS_MISSING, PARK>(f.nodes, f.tree_offset, f.tree_depth, t, my, B, idx, xb);
 #pragma unroll
     for (int j = 0; j < ILP; ++j) {
       if (PRED_LEAF) {
@@ -166,7 +189,7 @@ __global__ void __launch_bounds__(MAXT) predict_rows_kernel(DeviceForest f, Pred
   }
   for (; t < ntree; ++t) {
     uint32_t idx[1], xb[1];
-    walk_group<1, HAS_MISSING>(f.nodes, f.tree_offset, f.tree_depth, t, my, B, idx, xb);
+    walk_group<1, HAS_MISSING, PARK>(f.nodes, f.tree_offset, f.tree_depth, t, my, B, idx, xb);
     if (PRED_LEAF) {
       if (live) a.out[row * (uint64_t)ntree + t] = (float)__ldg(f.orig_id + idx[0]);
     } else {
@@ -176,24 +199,19 @@ __global__ void __launch_bounds__(MAXT) predict_rows_kernel(DeviceForest f, Pred
   if (!PRED_LEAF && live) a.out[row] = export_transform(acc, a.exp10, a.scale);
 }
 
-template <int ILP, bool LOCKSTEP, int MAXT>
+template <int ILP, bool PARK>
 static cudaError_t launch_predict_ilp(const DeviceForest &f, const PredictArgs &a, int block, cudaStream_t s) {
   // srow holds max(ncol, nfeat + 1) feature slots per thread
   const int slots = (f.nfeat + 1) > a.ncol ? (f.nfeat + 1) : a.ncol;
-  size_t smem = (size_t)block * slots * sizeof(float);
-  if (LOCKSTEP && smem < (size_t)116 * 1024) smem = (size_t)116 * 1024;  // > half an SM: one CTA per SM
+  const size_t smem = (size_t)block * slots * sizeof(float);
   const uint64_t nblk = (a.nrow + block - 1) / block;
   if (nblk > 0x7fffffffull) return cudaErrorInvalidConfiguration;
   const dim3 grid((unsigned)nblk);
 #define QC_GO(HM, PL)                                                                                            \
   do {                                                                                                           \
-    auto k = predict_rows_kernel<ILP, HM, PL, LOCKSTEP, MAXT>;                                                   \
+    auto k = predict_rows_kernel<ILP, HM, PL, PARK>;                                                             \
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);             \
     if (e != cudaSuccess) return e;                                                                              \
-    if (LOCKSTEP) {                                                                                              \
-      e = cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, 51);                           \
-      if (e != cudaSuccess) return e;                                                                            \
-    }                                                                                                            \
     k<<<grid, block, smem, s>>>(f, a);                                                                           \
   } while (0)
   if (a.pred_leaf) {
@@ -207,23 +225,15 @@ static cudaError_t launch_predict_ilp(const DeviceForest &f, const PredictArgs &
 
 cudaError_t launch_predict(const DeviceForest &f, const PredictArgs &a, const Tunables &t, cudaStream_t s) {
   if (a.nrow == 0) return cudaSuccess;
-  if (a.ncol > 32 || f.nfeat > 31) return cudaErrorInvalidValue;  // staged through 32 registers; capi.cpp reports it
-  if (t.variant == 1) {
-    int block = t.block > 0 ? (t.block + 31) / 32 * 32 : 1024;
-    if (block > 1024) block = 1024;
-    switch (t.ilp > 0 ? t.ilp : 1) {
-      case 2: return launch_predict_ilp<2, true, 1024>(f, a, block, s);
-      default: return launch_predict_ilp<1, true, 1024>(f, a, block, s);
-    }
-  }
+  if (a.ncol > 32 || f.nfeat > 31) return cudaErrorInvalidValue;  // staged through 32 registers (forest.hpp kMaxFeatures)
   int block = t.block > 0 ? t.block : 256;
   if (block > 256) block = 256;
   block = (block + 31) / 32 * 32;
-  switch (t.ilp > 0 ? t.ilp : 2) {
-    case 1: return launch_predict_ilp<1, false, 256>(f, a, block, s);
-    case 4: return launch_predict_ilp<4, false, 256>(f, a, block, s);
-    case 8: return launch_predict_ilp<8, false, 256>(f, a, block, s);
-    default: return launch_predict_ilp<2, false, 256>(f, a, block, s);
+  const bool park = t.park != 0;
+  switch (t.ilp > 0 ? t.ilp : 4) {
+    case 1: return park ? launch_predict_ilp<1, true>(f, a, block, s) : launch_predict_ilp<1, false>(f, a, block, s);
+    case 2: return park ? launch_predict_ilp<2, true>(f, a, block, s) : launch_predict_ilp<2, false>(f, a, block, s);
+    default: return park ? launch_predict_ilp<4, true>(f, a, block, s) : launch_predict_ilp<4, false>(f, a, block, s);
   }
 }
 

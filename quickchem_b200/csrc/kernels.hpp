@@ -37,6 +37,7 @@ struct Tunables {
   int ilp = 0;       // trees walked concurrently per thread (0 = default)
   int block = 0;     // threads per CTA (0 = default)
   int top_levels = 0;
+  int park = -1;     // -1 = default (on)
 };
 
 uint64_t launch_count();
