@@ -310,7 +310,7 @@ def main():
             sink[0] = float(res[0]) + float(res[n - 1])  # the host reads the result it was handed
             d.free()                                 # XGDMatrixFree_f (:377)
 
-        ms_e2e = wall(e2e_step, max(3, args.steps // 2), 2)
+        ms_e2e = wall(e2e_step, max(3, args.steps // 2), 3)
         e2e = {"value": total_cells / (ms_e2e * 1e-3), "unit": "cells/s", "h2d_bytes_per_step": ncell * NFEAT * 4 * world,
                "d2h_bytes_per_step": ncell * 4 * world, "ms_per_step": ms_e2e,
                "path": "XGDMatrixCreateFromMat+XGBoosterPredict+XGDMatrixFree, pinned host X, result read on host"}  # fmt: skip

@@ -2,6 +2,7 @@
 // Everything numerical is a kernel launch (kernels.cu); there is no CPU compute path.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -52,8 +53,13 @@ struct Error : std::runtime_error {
 struct Ctx {
   bool ready = false;
   int device = -1;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr;       // compute (and everything ordered with it)
+  cudaStream_t copy_stream = nullptr;  // H2D of matrix chunks
+  cudaStream_t d2h_stream = nullptr;   // D2H of result chunks
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  std::vector<cudaEvent_t> chunk_events;
+  int speculate = 1;                   // pipeline prediction into XGDMatrixCreateFromMat
+  uint64_t chunk_rows = 1ull << 21;
   void *flush = nullptr;
   size_t flush_bytes = 0;
   Tunables tun;
@@ -83,6 +89,8 @@ void ensure_device() {
     throw Error(std::string("libqcoh is built for sm_100a (B200); device '") + p.name + "' is sm_" + std::to_string(p.major) +
                 std::to_string(p.minor));
   CU(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
+  CU(cudaStreamCreateWithFlags(&g.copy_stream, cudaStreamNonBlocking));
+  CU(cudaStreamCreateWithFlags(&g.d2h_stream, cudaStreamNonBlocking));
   CU(cudaEventCreate(&g.ev0));
   CU(cudaEventCreate(&g.ev1));
   g.device = dev;
@@ -106,6 +114,13 @@ struct DevBuf {
     if (p) cudaFree(p);
     p = nullptr, cap = 0;
   }
+  void swap(DevBuf &o) {
+    std::swap(p, o.p);
+    std::swap(cap, o.cap);
+  }
+  DevBuf() = default;
+  DevBuf(const DevBuf &) = delete;
+  DevBuf &operator=(const DevBuf &) = delete;
   ~DevBuf() { release(); }
 };
 
@@ -122,6 +137,13 @@ struct PinBuf {
     }
     return p;
   }
+  void swap(PinBuf &o) {
+    std::swap(p, o.p);
+    std::swap(cap, o.cap);
+  }
+  PinBuf() = default;
+  PinBuf(const PinBuf &) = delete;
+  PinBuf &operator=(const PinBuf &) = delete;
   ~PinBuf() {
     if (p) cudaFreeHost(p);
   }
@@ -144,6 +166,7 @@ constexpr uint32_t kOhMagic = 0x51434f48;       // 'QCOH'
 
 struct Booster {
   uint32_t magic = kBoosterMagic;
+  uint64_t version = 0;  // changes with every (re)load
   bool loaded = false, uploaded = false;
   HostForest host;
   FlatForest flat;
@@ -163,12 +186,25 @@ struct DMatrix {
   DevBuf<int> flags;
   int hflags = 1;  // bit0 has-missing, bit1 has-inf; conservative until sealed
   bool sealed = false;
+  // prediction pipelined into XGDMatrixCreateFromMat (see create_pipelined)
+  const void *spec_booster = nullptr;
+  uint64_t spec_version = 0;
+  bool spec_ready = false;
+  DevBuf<float> spec_dev;
+  PinBuf<float> spec_host;
 };
 
 // XGDMatrixFree keeps the largest freed matrix buffer for the next XGDMatrixCreateFromMat: the
 // reference creates and frees a same-sized DMatrix on every call (OH_GridCompMod.F90:347,377) and
 // cudaMalloc / cudaFree of multi-GB buffers would otherwise dominate the step.
 DevBuf<float> g_spare_X;
+PinBuf<float> g_spare_pin;
+DevBuf<float> g_spare_spec;
+DevBuf<int> g_chunk_flags;
+PinBuf<int> g_h_chunk_flags;
+struct Booster;
+Booster *g_last_booster = nullptr;  // the process's booster (the reference keeps exactly one, SAVE :182)
+uint64_t g_version_counter = 0;
 
 Booster *B(BoosterHandle h) {
   Booster *b = (Booster *)h;
@@ -235,6 +271,83 @@ void predict_into(Booster *b, DMatrix *d, int option_mask, unsigned ntree_limit,
   CU(launch_predict(b->dev, a, g.tun, g.stream));
 }
 
+cudaEvent_t chunk_event(size_t i) {
+  while (g.chunk_events.size() <= i) {
+    cudaEvent_t e;
+    CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    g.chunk_events.push_back(e);
+  }
+  return g.chunk_events[i];
+}
+
+void drain() {
+  cudaStreamSynchronize(g.copy_stream);
+  cudaStreamSynchronize(g.stream);
+  cudaStreamSynchronize(g.d2h_stream);
+}
+
+// XGDMatrixCreateFromMat from HOST memory, pipelined: the matrix is cut into row chunks; while chunk
+// c+1 crosses PCIe, chunk c is scanned (missing / inf) and — since the reference keeps exactly one
+// booster per process and always predicts with option_mask = 0, ntree_limit = 0 right after creating
+// the matrix (OH_GridCompMod.F90:347-356) — already predicted with that booster, and its results
+// stream back into a pinned buffer.  XGBoosterPredict then finds the answer ready if it is called
+// with that booster and those options; any other call takes the ordinary path.  The caller's buffer
+// is fully consumed (all H2D copies complete) before this returns.
+void create_pipelined(DMatrix *d, const float *data, Booster *b) {
+  const uint64_t nrow = d->nrow, ncol = d->ncol;
+  const uint64_t cr = g.chunk_rows;
+  const size_t nchunk = (size_t)((nrow + cr - 1) / cr);
+  float *X = d->X.p;
+  const bool spec = b != nullptr;
+  float *sdev = nullptr, *shost = nullptr;
+  if (spec) {
+    upload(b);
+    if (g_spare_spec.cap >= nrow && g_spare_spec.p) d->spec_dev.swap(g_spare_spec);
+    sdev = d->spec_dev.need(nrow);
+    if (g_spare_pin.cap >= nrow && g_spare_pin.p) d->spec_host.swap(g_spare_pin);
+    shost = d->spec_host.need(nrow);
+  }
+  int *fl = g_chunk_flags.need(nchunk);
+  int *hfl = g_h_chunk_flags.need(nchunk);
+  CU(cudaMemsetAsync(fl, 0, nchunk * sizeof(int), g.stream));
+  for (size_t c = 0; c < nchunk; ++c) {
+    const uint64_t r0 = c * cr, nr = std::min(cr, nrow - r0);
+    CU(cudaMemcpyAsync(X + r0 * ncol, data + r0 * ncol, nr * ncol * sizeof(float), cudaMemcpyHostToDevice, g.copy_stream));
+    CU(cudaEventRecord(chunk_event(3 * c), g.copy_stream));
+  }
+  int flags = 0;
+  for (size_t c = 0; c < nchunk; ++c) {
+    const uint64_t r0 = c * cr, nr = std::min(cr, nrow - r0);
+    CU(cudaStreamWaitEvent(g.stream, chunk_event(3 * c), 0));
+    CU(launch_scan_matrix(X + r0 * ncol, nr * ncol, d->missing, fl + c, g.stream));
+    CU(cudaMemcpyAsync(hfl + c, fl + c, sizeof(int), cudaMemcpyDeviceToHost, g.stream));
+    CU(cudaEventRecord(chunk_event(3 * c + 1), g.stream));
+    CU(cudaEventSynchronize(chunk_event(3 * c + 1)));
+    flags |= hfl[c];
+    if (hfl[c] & 2) {
+      drain();
+      throw Error("Check failed: valid: Input data contains `inf` or `nan`");
+    }
+    if (spec) {
+      PredictArgs a;
+      a.X = X + r0 * ncol, a.nrow = nr, a.ncol = (int32_t)ncol, a.missing = d->missing;
+      a.has_missing = ((hfl[c] & 1) || ncol < b->host.num_feature) ? 1 : 0;
+      a.ntree_used = (int32_t)b->host.trees.size();
+      a.out = sdev + r0;
+      CU(launch_predict(b->dev, a, g.tun, g.stream));
+      CU(cudaEventRecord(chunk_event(3 * c + 2), g.stream));
+      CU(cudaStreamWaitEvent(g.d2h_stream, chunk_event(3 * c + 2), 0));
+      CU(cudaMemcpyAsync(shost + r0, sdev + r0, nr * sizeof(float), cudaMemcpyDeviceToHost, g.d2h_stream));
+    }
+  }
+  CU(cudaStreamSynchronize(g.copy_stream));  // the borrowed host buffer has been read completely
+  d->hflags = flags;
+  d->sealed = true;
+  if (spec) {
+    d->spec_booster = b, d->spec_version = b->version, d->spec_ready = true;
+  }
+}
+
 }  // namespace
 
 // =====================================================================================
@@ -257,6 +370,8 @@ int XGBoosterCreate(const DMatrixHandle dmats[], bst_ulong len, BoosterHandle *o
 int XGBoosterFree(BoosterHandle handle) {
   API_BEGIN
   Booster *b = B(handle);
+  if (g_last_booster == b) g_last_booster = nullptr;
+  if (g.ready) CU(cudaStreamSynchronize(g.stream));
   b->magic = 0;
   delete b;
   API_END
@@ -270,6 +385,7 @@ int qcoh_booster_parse(BoosterHandle handle, const char *fname) {
   FlatForest ff = flatten(hf);
   b->host = std::move(hf), b->flat = std::move(ff);
   b->loaded = true, b->uploaded = false;
+  b->version = ++g_version_counter;
   API_END
 }
 
@@ -277,6 +393,7 @@ int XGBoosterLoadModel(BoosterHandle handle, const char *fname) {
   if (qcoh_booster_parse(handle, fname) != 0) return -1;
   API_BEGIN
   upload(B(handle));
+  g_last_booster = B(handle);
   API_END
 }
 
@@ -296,15 +413,21 @@ int XGDMatrixCreateFromMat(const float *data, bst_ulong nrow, bst_ulong ncol, fl
   std::unique_ptr<DMatrix> d(new DMatrix());
   d->nrow = nrow, d->ncol = ncol, d->missing = missing;
   const size_t n = (size_t)nrow * ncol;
-  if (g_spare_X.cap >= n && g_spare_X.p) std::swap(d->X, g_spare_X);
+  if (g_spare_X.cap >= n && g_spare_X.p) d->X.swap(g_spare_X);
   d->X.need(n);
-  if (n) {
-    // borrowed for this call only (the reference deallocates xx_carr right after predict,
-    // OH_GridCompMod.F90:383): copy to HBM now, synchronously.
-    CU(cudaMemcpyAsync(d->X.p, data, n * sizeof(float), is_device_ptr(data) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, g.stream));
-    CU(cudaStreamSynchronize(g.stream));
+  // borrowed for this call only (the reference deallocates xx_carr right after predict,
+  // OH_GridCompMod.F90:383): the data is in HBM when this returns.
+  if (n && !is_device_ptr(data)) {
+    Booster *b = g.speculate ? g_last_booster : nullptr;
+    if (b && !(b->loaded && ncol <= b->host.num_feature)) b = nullptr;
+    create_pipelined(d.get(), data, b);
+  } else {
+    if (n) {
+      CU(cudaMemcpyAsync(d->X.p, data, n * sizeof(float), cudaMemcpyDeviceToDevice, g.stream));
+      CU(cudaStreamSynchronize(g.stream));
+    }
+    seal(d.get());
   }
-  seal(d.get());
   *out = d.release();
   API_END
 }
@@ -312,8 +435,11 @@ int XGDMatrixCreateFromMat(const float *data, bst_ulong nrow, bst_ulong ncol, fl
 int XGDMatrixFree(DMatrixHandle handle) {
   API_BEGIN
   DMatrix *d = D(handle);
+  if (d->spec_ready) drain();  // pipelined work may still reference the buffers
   d->magic = 0;
-  if (d->X.cap > g_spare_X.cap) std::swap(d->X, g_spare_X);
+  if (d->X.cap > g_spare_X.cap) d->X.swap(g_spare_X);
+  if (d->spec_host.cap > g_spare_pin.cap) d->spec_host.swap(g_spare_pin);
+  if (d->spec_dev.cap > g_spare_spec.cap) d->spec_dev.swap(g_spare_spec);
   delete d;
   API_END
 }
@@ -340,6 +466,17 @@ int XGBoosterPredict(BoosterHandle handle, DMatrixHandle dmat, int option_mask, 
   if (!b->loaded) throw Error("Booster has no model: call XGBoosterLoadModel first");
   const size_t n = (size_t)d->nrow * ((option_mask & 2) ? trees_used(b, ntree_limit) : 1);
   ensure_device();
+  g_last_booster = b;
+  if (d->spec_ready && d->spec_booster == b && d->spec_version == b->version && (option_mask & ~1) == 0 &&
+      trees_used(b, ntree_limit) == b->host.trees.size()) {
+    // already predicted while the matrix was crossing PCIe: adopt the pinned result buffer
+    CU(cudaStreamSynchronize(g.d2h_stream));
+    b->h_result.swap(d->spec_host);
+    d->spec_ready = false;
+    *out_len = n;
+    *out_result = b->h_result.p;
+    return 0;
+  }
   float *dv = b->d_result.need(n);
   float *hv = b->h_result.need(n);
   predict_into(b, d, option_mask, ntree_limit, nullptr, dv);
@@ -496,6 +633,8 @@ int qcoh_set_param(const char *name, const char *value) {
   else if (n == "block") g.tun.block = v;
   else if (n == "top_levels") g.tun.top_levels = v;
   else if (n == "park") g.tun.park = v;
+  else if (n == "speculate") g.speculate = v;
+  else if (n == "chunk_rows") g.chunk_rows = v > 0 ? ((uint64_t)v + 255) / 256 * 256 : (1ull << 21);
   else throw Error("qcoh_set_param: unknown parameter '" + n + "'");
   API_END
 }

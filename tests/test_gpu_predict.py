@@ -212,6 +212,60 @@ def test_kernel_variants_agree(capi, oracle, small_model_path, small_forest):
         capi.set_param("block", 0)
 
 
+def test_pipelined_create_matches_plain_path(capi, oracle, tmp_path, small_model_path, small_forest):
+    """XGDMatrixCreateFromMat pipelines H2D chunks with prediction by the process's booster; the
+    answer must be the same as the plain path, and any other booster / option must not see it."""
+    rng = np.random.default_rng(9)
+    x = inject_specials(synth.quick_features(synth.raw_fields(8)), small_forest, rng)
+    ref = oracle.Model(small_model_path).predict(x)
+    other = synth.random_forest_structure(7, 6, seed=21)
+    p2 = str(tmp_path / "other.model")
+    xgbmodel.write_legacy_binary(other, p2)
+    ref2 = oracle.Model(p2).predict(x)
+    try:
+        for chunk in (256, 1024, 1 << 21):
+            capi.set_param("chunk_rows", chunk)
+            for spec in (0, 1):
+                capi.set_param("speculate", spec)
+                b = capi.Booster(small_model_path)  # becomes the process's booster
+                d = capi.DMatrix(x)
+                assert np.array_equal(b.predict(d).view(np.uint32), ref.view(np.uint32)), (chunk, spec)
+                assert np.array_equal(b.predict(d).view(np.uint32), ref.view(np.uint32))  # second call: plain path
+                leaf = b.predict(capi.DMatrix(x), option_mask=2)  # options the pipeline did not assume
+                assert leaf.shape == (x.shape[0], small_forest.num_trees)
+                lim = b.predict(capi.DMatrix(x), ntree_limit=3)
+                assert np.array_equal(lim.view(np.uint32), oracle.Model(small_model_path).predict(x, ntree_limit=3).view(np.uint32))
+                b2 = capi.Booster(p2)  # now the last-loaded booster
+                d2 = capi.DMatrix(x)   # pipelined for b2 ...
+                assert np.array_equal(b.predict(d2).view(np.uint32), ref.view(np.uint32))   # ... asked of b
+                assert np.array_equal(b2.predict(d2).view(np.uint32), ref2.view(np.uint32))
+        capi.set_param("speculate", 1)
+        xi = x.copy()
+        xi[-1, 3] = np.inf  # inf in the last chunk still fails the create call
+        capi.set_param("chunk_rows", 1024)
+        with pytest.raises(capi.QcohError, match="inf"):
+            capi.DMatrix(xi)
+    finally:
+        capi.set_param("chunk_rows", 0)
+        capi.set_param("speculate", 1)
+
+
+def test_result_buffer_lifetime(capi, small_model_path):
+    """The prediction buffer belongs to the booster and stays valid until its next predict — also
+    across the creation of the next matrix (which is pipelined into another pinned buffer)."""
+    x1 = synth.quick_features(synth.raw_fields(6))
+    x2 = x1[::-1].copy()
+    b = capi.Booster(small_model_path)
+    d1 = capi.DMatrix(x1)
+    n, p = b.predict_raw(d1)
+    first = np.ctypeslib.as_array(p, (n,)).copy()
+    d2 = capi.DMatrix(x2)  # must not clobber p
+    assert np.array_equal(np.ctypeslib.as_array(p, (n,)), first)
+    d1.free()
+    assert np.array_equal(np.ctypeslib.as_array(p, (n,)), first)
+    assert np.array_equal(b.predict(d2), first[::-1])
+
+
 def test_dmatrix_file_roundtrip(capi, tmp_path, small_model_path):
     x = synth.quick_features(synth.raw_fields(4))
     d = capi.DMatrix(x)
