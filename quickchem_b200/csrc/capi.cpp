@@ -633,6 +633,7 @@ int qcoh_set_param(const char *name, const char *value) {
   else if (n == "block") g.tun.block = v;
   else if (n == "top_levels") g.tun.top_levels = v;
   else if (n == "park") g.tun.park = v;
+  else if (n == "minb") g.tun.minb = v;
   else if (n == "speculate") g.speculate = v;
   else if (n == "chunk_rows") g.chunk_rows = v > 0 ? ((uint64_t)v + 255) / 256 * 256 : (1ull << 21);
   else throw Error("qcoh_set_param: unknown parameter '" + n + "'");

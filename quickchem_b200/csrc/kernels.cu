@@ -73,57 +73,58 @@ cudaError_t launch_fill(float *p, uint64_t n, float v, cudaStream_t s) {
 // XGBoost semantics restated (xgboost 1.6.0 src/predictor/predict_fn.h GetNextNode,
 // src/predictor/cpu_predictor.cc PredictByAllTrees): missing -> default child, else
 // left + !(fvalue < split_cond); out = base_score, then += leaf value tree by tree in float32.
+constexpr int kBlock = 256;  // rows per CTA; the feature stride in the transposed tile is kBlock floats
+
+// 0xFFFFFFFF if !(v < thr) (i.e. v >= thr or unordered), else 0 — one FSET, no predicate register
+__device__ __forceinline__ uint32_t right_mask(float v, float thr) {
+  uint32_t m;
+  asm("set.geu.u32.f32 %0, %1, %2;" : "=r"(m) : "f"(v), "f"(thr));
+  return m;
+}
+
 template <int ILP, bool HAS_MISSING, bool PARK>
 __device__ __forceinline__ void walk_group(const uint2 *__restrict__ nodes, const uint32_t *__restrict__ toff,
-                                           const int32_t *__restrict__ tdepth, int t, const float *my, int fstride,
+                                           const int32_t *__restrict__ tdepth, int t, uint32_t my_saddr,
                                            uint32_t (&idx)[ILP], uint32_t (&xbits)[ILP]) {
   int depth = 0;
+  uint2 nd[ILP];
+  uint32_t rel[ILP];
 #pragma unroll
   for (int j = 0; j < ILP; ++j) {
     idx[j] = __ldg(toff + t + j);
     depth = max(depth, __ldg(tdepth + t + j));
-    xbits[j] = 0;
+    nd[j] = make_uint2(0u, 0u);
+    rel[j] = 1u;
   }
-  if (PARK) {
-    // Lanes that have reached their leaf stop fetching: a parked lane would otherwise re-read its
-    // own leaf sector on every remaining level, and at the deep levels those are 32 different
-    // sectors per warp request — the L1TEX data stage is the bound of this kernel.
-    bool done[ILP];
-#pragma unroll
-    for (int j = 0; j < ILP; ++j) done[j] = false;
-    for (int d = 0; d <= depth; ++d) {
-#pragma unroll
-      for (int j = 0; j < ILP; ++j) {
-        if (!done[j]) {
-          const uint2 nd = __ldg(nodes + idx[j]);
-          const float v = my[(nd.y >> kMetaFeatShift) * fstride];
-          bool right = !(v < __uint_as_float(nd.x));
-          if (HAS_MISSING) {
-            if (v != v) right = !(nd.y & kMetaDefaultLeftBit);
-          }
-          const uint32_t rel = nd.y & kMetaRelMask;
-          idx[j] += rel + (right ? 1u : 0u);
-          xbits[j] = nd.x;
-          done[j] = rel == 0;
-        }
-      }
-    }
-    return;
-  }
-  // depth + 1 fetches: the last one reads the leaf itself, whose x word is the leaf value
+  // depth + 1 fetches per tree: the last one reads the leaf itself, whose x word is the leaf value.
+  // PARK: a lane that has reached its leaf (rel == 0) stops fetching — it would otherwise re-read its
+  // own leaf line at every remaining level, and at the deep levels those are up to 32 different
+  // lines per warp request; the L1TEX data pipe is the bound of this kernel.  The
+  // fetch is predicated, so nd[j] keeps the leaf node and no per-level copy of the value is needed.
   for (int d = 0; d <= depth; ++d) {
 #pragma unroll
     for (int j = 0; j < ILP; ++j) {
-      const uint2 nd = __ldg(nodes + idx[j]);
-      const float v = my[(nd.y >> kMetaFeatShift) * fstride];
-      bool right = !(v < __uint_as_float(nd.x));
-      if (HAS_MISSING) {
-        if (v != v) right = !(nd.y & kMetaDefaultLeftBit);
+      if (!PARK || rel[j] != 0u) {
+        nd[j] = __ldg(nodes + idx[j]);
+        // shared address of srow[feat][tid] = my_saddr + feat * (kBlock * 4): feat sits in the top byte
+        // of the meta word, so the high half of meta * 2^(log2(kBlock*4) + 8) is feat * kBlock * 4; one
+        // IMAD.WIDE with the thread's base address in the high word of the addend does it all
+        static_assert(kBlock * 4 == 1024 && kMetaFeatShift == 24, "address trick assumes 1 KB feature stride");
+        const uint64_t prod = (uint64_t)(nd[j].y & 0xFF000000u) * 1024u * 256u + ((uint64_t)my_saddr << 32);
+        const uint32_t sa = (uint32_t)(prod >> 32);
+        float v;
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(sa));
+        uint32_t m = right_mask(v, __uint_as_float(nd[j].x));
+        if (HAS_MISSING) {
+          if (v != v) m = (nd[j].y & kMetaDefaultLeftBit) ? 0u : 0xFFFFFFFFu;
+        }
+        rel[j] = nd[j].y & kMetaRelMask;
+        idx[j] = idx[j] + rel[j] - m;
       }
-      idx[j] += (nd.y & kMetaRelMask) + (right ? 1u : 0u);
-      xbits[j] = nd.x;
     }
   }
+#pragma unroll
+  for (int j = 0; j < ILP; ++j) xbits[j] = nd[j].x;
 }
 
 __device__ __forceinline__ float export_transform(float acc, int exp10_on, float scale) {
@@ -134,11 +135,11 @@ __device__ __forceinline__ float export_transform(float acc, int exp10_on, float
   return __fmul_rn(p, scale);
 }
 
-template <int ILP, bool HAS_MISSING, bool PRED_LEAF, bool PARK>
-__global__ void __launch_bounds__(256, 6) predict_rows_kernel(DeviceForest f, PredictArgs a) {
+template <int ILP, bool HAS_MISSING, bool PRED_LEAF, bool PARK, int MINB>
+__global__ void __launch_bounds__(kBlock, MINB) predict_rows_kernel(DeviceForest f, PredictArgs a) {
   extern __shared__ float srow[];
   const int tid = threadIdx.x;
-  const int B = blockDim.x;
+  constexpr int B = kBlock;
   const uint64_t r0 = (uint64_t)blockIdx.x * B;
   const uint64_t left = a.nrow - r0;
   const int nr = left < (uint64_t)B ? (int)left : B;
@@ -170,14 +171,14 @@ __global__ void __launch_bounds__(256, 6) predict_rows_kernel(DeviceForest f, Pr
   }
   if (tid >= nr) return;
   const bool live = true;
-  const float *my = srow + tid;
+  const uint32_t my = (uint32_t)__cvta_generic_to_shared(srow + tid);
   const uint64_t row = r0 + tid;
   const int ntree = a.ntree_used;
   float acc = f.base_score;
   int t = 0;
   for (; t + ILP <= ntree; t += ILP) {
     uint32_t idx[ILP], xb[ILP];
-    walk_group<ILP, HAS_MISSING, PARK>(f.nodes, f.tree_offset, f.tree_depth, t, my, B, idx, xb);
+    walk_group<ILP, HAS_MISSING, PARK>(f.nodes, f.tree_offset, f.tree_depth, t, my, idx, xb);
 #pragma unroll
     for (int j = 0; j < ILP; ++j) {
       if (PRED_LEAF) {
@@ -189,7 +190,7 @@ __global__ void __launch_bounds__(256, 6) predict_rows_kernel(DeviceForest f, Pr
   }
   for (; t < ntree; ++t) {
     uint32_t idx[1], xb[1];
-    walk_group<1, HAS_MISSING, PARK>(f.nodes, f.tree_offset, f.tree_depth, t, my, B, idx, xb);
+    walk_group<1, HAS_MISSING, PARK>(f.nodes, f.tree_offset, f.tree_depth, t, my, idx, xb);
     if (PRED_LEAF) {
       if (live) a.out[row * (uint64_t)ntree + t] = (float)__ldg(f.orig_id + idx[0]);
     } else {
@@ -199,42 +200,37 @@ __global__ void __launch_bounds__(256, 6) predict_rows_kernel(DeviceForest f, Pr
   if (!PRED_LEAF && live) a.out[row] = export_transform(acc, a.exp10, a.scale);
 }
 
-template <int ILP, bool PARK>
-static cudaError_t launch_predict_ilp(const DeviceForest &f, const PredictArgs &a, int block, cudaStream_t s) {
+template <int ILP, bool HM, bool PL, bool PARK, int MINB>
+static cudaError_t launch_predict_one(const DeviceForest &f, const PredictArgs &a, cudaStream_t s) {
   // srow holds max(ncol, nfeat + 1) feature slots per thread
   const int slots = (f.nfeat + 1) > a.ncol ? (f.nfeat + 1) : a.ncol;
-  const size_t smem = (size_t)block * slots * sizeof(float);
-  const uint64_t nblk = (a.nrow + block - 1) / block;
+  const size_t smem = (size_t)kBlock * slots * sizeof(float);
+  const uint64_t nblk = (a.nrow + kBlock - 1) / kBlock;
   if (nblk > 0x7fffffffull) return cudaErrorInvalidConfiguration;
-  const dim3 grid((unsigned)nblk);
-#define QC_GO(HM, PL)                                                                                            \
-  do {                                                                                                           \
-    auto k = predict_rows_kernel<ILP, HM, PL, PARK>;                                                             \
-    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);             \
-    if (e != cudaSuccess) return e;                                                                              \
-    k<<<grid, block, smem, s>>>(f, a);                                                                           \
-  } while (0)
-  if (a.pred_leaf) {
-    if (a.has_missing) QC_GO(true, true); else QC_GO(false, true);
-  } else {
-    if (a.has_missing) QC_GO(true, false); else QC_GO(false, false);
-  }
-#undef QC_GO
+  auto k = predict_rows_kernel<ILP, HM, PL, PARK, MINB>;
+  cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  k<<<dim3((unsigned)nblk), kBlock, smem, s>>>(f, a);
   return QC_LAUNCHED();
 }
 
 cudaError_t launch_predict(const DeviceForest &f, const PredictArgs &a, const Tunables &t, cudaStream_t s) {
   if (a.nrow == 0) return cudaSuccess;
   if (a.ncol > 32 || f.nfeat > 31) return cudaErrorInvalidValue;  // staged through 32 registers (forest.hpp kMaxFeatures)
-  int block = t.block > 0 ? t.block : 256;
-  if (block > 256) block = 256;
-  block = (block + 31) / 32 * 32;
-  const bool park = t.park != 0;
-  switch (t.ilp > 0 ? t.ilp : 4) {
-    case 1: return park ? launch_predict_ilp<1, true>(f, a, block, s) : launch_predict_ilp<1, false>(f, a, block, s);
-    case 2: return park ? launch_predict_ilp<2, true>(f, a, block, s) : launch_predict_ilp<2, false>(f, a, block, s);
-    default: return park ? launch_predict_ilp<4, true>(f, a, block, s) : launch_predict_ilp<4, false>(f, a, block, s);
-  }
+  if (a.pred_leaf)
+    return a.has_missing ? launch_predict_one<4, true, true, true, 6>(f, a, s) : launch_predict_one<4, false, true, true, 6>(f, a, s);
+  if (a.has_missing) return launch_predict_one<4, true, false, true, 6>(f, a, s);
+  // clean matrix, sums: the production path; ILP / residency are tunable for experiments
+  if (t.park == 0) return launch_predict_one<4, false, false, false, 6>(f, a, s);
+  const int ilp = t.ilp > 0 ? t.ilp : 3, minb = t.minb > 0 ? t.minb : 6;
+#define QC_CASE(I, M) \
+  if (ilp == I && minb == M) return launch_predict_one<I, false, false, true, M>(f, a, s);
+  QC_CASE(1, 6) QC_CASE(2, 6) QC_CASE(3, 6) QC_CASE(4, 6) QC_CASE(6, 6)
+  QC_CASE(2, 5) QC_CASE(3, 5) QC_CASE(4, 5) QC_CASE(6, 5)
+  QC_CASE(2, 4) QC_CASE(3, 4) QC_CASE(4, 4) QC_CASE(6, 4) QC_CASE(8, 4)
+  QC_CASE(4, 3) QC_CASE(6, 3) QC_CASE(8, 3)
+#undef QC_CASE
+  return launch_predict_one<4, false, false, true, 6>(f, a, s);
 }
 
 // =====================================================================================

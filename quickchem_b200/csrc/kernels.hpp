@@ -38,6 +38,7 @@ struct Tunables {
   int block = 0;     // threads per CTA (0 = default)
   int top_levels = 0;
   int park = -1;     // -1 = default (on)
+  int minb = 0;      // min resident CTAs per SM the kernel is compiled for (register budget)
 };
 
 uint64_t launch_count();
