@@ -196,20 +196,24 @@ def test_device_resident_predict_and_epilogue(capi, oracle, small_model_path, sm
 
 
 def test_kernel_variants_agree(capi, oracle, small_model_path, small_forest):
-    rng = np.random.default_rng(3)
-    x = inject_specials(synth.quick_features(synth.raw_fields(8)), small_forest, rng)
+    """Every tunable build of the predict kernel (trees in flight, residency target, parked lanes on/off)
+    gives the same bits; the clean matrix exercises the no-missing specialisation."""
+    x = synth.quick_features(synth.raw_fields(8))
     ref = oracle.Model(small_model_path).predict(x)
     b = capi.Booster(small_model_path)
     d = capi.DMatrix(x)
     try:
-        for ilp in (1, 2, 4, 8):
-            for block in (64, 128, 256):
-                capi.set_param("ilp", ilp)
-                capi.set_param("block", block)
-                assert np.array_equal(b.predict(d).view(np.uint32), ref.view(np.uint32)), (ilp, block)
+        for park in (0, 1):
+            capi.set_param("park", park)
+            for ilp in (1, 2, 3, 4, 6, 8):
+                for minb in (3, 4, 5, 6):
+                    capi.set_param("ilp", ilp)
+                    capi.set_param("minb", minb)
+                    assert np.array_equal(b.predict(d).view(np.uint32), ref.view(np.uint32)), (park, ilp, minb)
     finally:
         capi.set_param("ilp", 0)
-        capi.set_param("block", 0)
+        capi.set_param("minb", 0)
+        capi.set_param("park", -1)
 
 
 def test_pipelined_create_matches_plain_path(capi, oracle, tmp_path, small_model_path, small_forest):
@@ -290,3 +294,27 @@ def test_linearity_property_full_size(capi, small_model_path):
     assert np.array_equal(full, np.concatenate([a, c]))
     perm = np.random.default_rng(0).permutation(x.shape[0])[:500000]
     assert np.array_equal(b.predict(capi.DMatrix(x[perm])), full[perm])
+
+
+def test_replication_property_c360_size(capi, small_model_path):
+    """BASELINE.json configs[2] size (C360 x 72 = 55 987 200 rows, 6 GB of features) without
+    generating 6 GB on the host: the C90 matrix is uploaded 16 times into one device-resident
+    DMatrix; every replica must reproduce the first one's predictions bit for bit (rows are
+    independent, tiles and chunk boundaries fall differently in every replica)."""
+    x = synth.quick_features(synth.raw_fields(90))
+    n = x.shape[0]
+    reps = 16
+    b = capi.Booster(small_model_path)
+    d = capi.DMatrix.device(n * reps, 27)
+    for r in range(reps):
+        d.upload(x, r * n)
+    d.seal()
+    assert d.num_row == 55987200
+    out = capi.DeviceArray(n * reps)
+    b.predict_device(d, out)
+    capi.synchronize()
+    got = out.get().reshape(reps, n)
+    first = b.predict(capi.DMatrix(x))
+    for r in range(reps):
+        assert np.array_equal(got[r].view(np.uint32), first.view(np.uint32)), r
+

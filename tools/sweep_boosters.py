@@ -1,0 +1,94 @@
+#!/usr/bin/env python
+"""BASELINE.json configs[4]: C180 x 72 with device-resident fields — (a) booster sweep trees x depth:
+cells/s, node visits per cell and fraction of the HBM roofline (112 B/cell) of the predict
+kernel; (b) one model day of 24 hourly steps with compute_once_per_day (1 boost step + 23 steps that
+reuse the persistent OH_ML), fields resident in HBM.
+    python tools/sweep_boosters.py [--grid 180] [--grow-only]"""
+import argparse, json, os, sys, time
+import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from quickchem_b200 import synth, xgbmodel
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--grid", type=int, default=180)
+ap.add_argument("--grow-only", action="store_true")
+ap.add_argument("--trees", default="10,30,100")
+ap.add_argument("--depths", default="6,10,14,18")
+a = ap.parse_args()
+os.makedirs(os.path.join(ROOT, "build"), exist_ok=True)
+combos = [(t, d) for t in map(int, a.trees.split(",")) for d in map(int, a.depths.split(","))]
+paths = {}
+for t, d in combos:
+    p = os.path.join(ROOT, "build", f"oh_booster_{t}x{d}.model")
+    if not os.path.exists(p):
+        t0 = time.time()
+        f = synth.prod_like_booster(n_trees=t, max_depth=d)
+        xgbmodel.write_legacy_binary(f, p)
+        print(f"grew {t}x{d}: {f.total_nodes()} nodes in {time.time()-t0:.0f}s", file=sys.stderr, flush=True)
+    paths[(t, d)] = p
+if a.grow_only:
+    sys.exit(0)
+
+from quickchem_b200 import capi
+peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs", 6650.0) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
+fields = synth.raw_fields(a.grid)
+km, ncol = fields["T"].shape
+ncell = km * ncol
+dev = {k: capi.DeviceArray(v) for k, v in fields.items()}
+out = capi.DeviceArray(ncell)
+rows = []
+dX = None
+for (t, d), p in paths.items():
+    b = capi.Booster(p)
+    info = b.info()
+    if dX is None:  # assemble X once on the device with the fused path
+        oh = capi.OhRun1(b, ncol, km, synth.MAPL, tropp_min=0.0)
+        dX = capi.DMatrix.device(ncell, 27)
+        xp = capi.vp(); capi.check(capi.lib().qcoh_dmatrix_device_ptr(dX.handle, capi.C.byref(xp)))
+        ro = capi.Run1Out(); oh_out = capi.DeviceArray(ncell); ro.OH = oh_out.ptr; ro.X = xp
+        rin = oh.make_in(dev)
+        capi.check(capi.lib().qcoh_oh_run1(oh.handle, capi.C.byref(rin), capi.C.byref(ro)))
+        dX.seal()
+        hx = np.empty((1 << 16, 27), np.float32)
+        capi.check(capi.lib().qcoh_memcpy_d2h(hx.ctypes.data_as(capi.vp), xp, hx.nbytes))
+    for _ in range(3):
+        b.predict_device(dX, out, exp10=True, scale=0.85)
+    capi.synchronize(); capi.timer_start()
+    n = 10
+    for _ in range(n):
+        b.predict_device(dX, out, exp10=True, scale=0.85)
+    ms = capi.timer_stop() / n
+    # mean visited depth from leaf ids of a sample (device leaf-index output)
+    leaf = b.predict(capi.DMatrix(hx[:4096]), option_mask=2).astype(np.int64)
+    nodes, off, depth, orig = b.flat()
+    pos = np.empty(int(off[-1]), np.int64)
+    visits = 0.0
+    for ti in range(info.num_trees):
+        n0, n1 = int(off[ti]), int(off[ti + 1])
+        meta = nodes[n0:n1, 1]; rel = (meta & ((1 << 23) - 1)).astype(np.int64)
+        dep = np.zeros(n1 - n0, np.int32)
+        idx = np.nonzero(rel)[0]
+        for i in idx:  # BFS order: parents before children
+            dep[i + rel[i]] = dep[i] + 1; dep[i + rel[i] + 1] = dep[i] + 1
+        lut = np.empty(n1 - n0, np.int64); lut[orig[n0:n1]] = np.arange(n1 - n0)
+        visits += dep[lut[leaf[:, ti]]].mean() + 1
+    gbs = ncell * 112 / 1e9 / (ms * 1e-3)
+    rows.append(dict(trees=t, max_depth=d, nodes=int(info.num_nodes), visits_per_cell=round(visits, 1), ms=round(ms, 3),
+                     cells_per_s=ncell / (ms * 1e-3), hbm_gbs=round(gbs, 1), hbm_frac=round(gbs / peak, 4)))
+    print(json.dumps(rows[-1]), flush=True)
+    b.free()
+
+# (b) one model day: 24 hourly steps, compute_once_per_day
+b = capi.Booster(paths[max(paths)])
+oh = capi.OhRun1(b, ncol, km, synth.MAPL)  # 40 hPa slab as in production
+ro = capi.Run1Out(); ro.OH = oh_out.ptr
+t_steps = []
+for hour in range(24):
+    rin = oh.make_in(dev, nymd=20220701, need_to_call_boost=(hour == 0))
+    capi.synchronize(); t0 = time.perf_counter()
+    capi.check(capi.lib().qcoh_oh_run1(oh.handle, capi.C.byref(rin), capi.C.byref(ro)))
+    t_steps.append((time.perf_counter() - t0) * 1e3)
+print(json.dumps(dict(day="24 hourly steps, compute_once_per_day, device-resident fields", grid=a.grid, k1=ro.k1,
+                      boost_step_ms=round(t_steps[0], 2), other_step_ms=round(float(np.median(t_steps[1:])), 3),
+                      day_ms=round(sum(t_steps), 2))), flush=True)
