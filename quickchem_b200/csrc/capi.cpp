@@ -286,16 +286,56 @@ void drain() {
   cudaStreamSynchronize(g.d2h_stream);
 }
 
+bool is_pinned_host(const void *p) {
+  cudaPointerAttributes a;
+  cudaError_t e = cudaPointerGetAttributes(&a, p);
+  if (e != cudaSuccess) {
+    (void)cudaGetLastError();
+    return false;
+  }
+  return a.type == cudaMemoryTypeHost;
+}
+
+// multi-threaded memcpy (pageable host -> pinned staging)
+void parallel_memcpy(void *dst, const void *src, size_t bytes) {
+  unsigned nt = std::thread::hardware_concurrency();
+  if (nt == 0) nt = 1;
+  if (nt > 16) nt = 16;
+  if (bytes < ((size_t)8 << 20)) nt = 1;
+  if (nt == 1) {
+    memcpy(dst, src, bytes);
+    return;
+  }
+  std::vector<std::thread> th;
+  const size_t per = (bytes / nt + 4095) / 4096 * 4096;
+  for (unsigned t = 0; t < nt; ++t) {
+    const size_t o = (size_t)t * per;
+    if (o >= bytes) break;
+    const size_t n = std::min(per, bytes - o);
+    th.emplace_back([=] { memcpy((char *)dst + o, (const char *)src + o, n); });
+  }
+  for (auto &t : th) t.join();
+}
+
+constexpr int kStageSlots = 3;
+PinBuf<float> g_stage[kStageSlots];
+cudaEvent_t g_stage_free[kStageSlots] = {nullptr, nullptr, nullptr};
+
 // XGDMatrixCreateFromMat from HOST memory, pipelined: the matrix is cut into row chunks; while chunk
 // c+1 crosses PCIe, chunk c is scanned (missing / inf) and — since the reference keeps exactly one
 // booster per process and always predicts with option_mask = 0, ntree_limit = 0 right after creating
 // the matrix (OH_GridCompMod.F90:347-356) — already predicted with that booster, and its results
 // stream back into a pinned buffer.  XGBoosterPredict then finds the answer ready if it is called
-// with that booster and those options; any other call takes the ordinary path.  The caller's buffer
-// is fully consumed (all H2D copies complete) before this returns.
+// with that booster and those options; any other call takes the ordinary path.  Pageable host
+// memory (what a Fortran ALLOCATE gives) is staged through a ring of pinned buffers by a threaded
+// memcpy so that the DMA engine never waits on the driver's own bounce buffer.  The caller's buffer
+// is fully consumed before this returns.
+//   copy_stream : H2D(c) -> scan(c) -> flag D2H(c)      g.stream : predict(c)      d2h_stream : result D2H(c)
 void create_pipelined(DMatrix *d, const float *data, Booster *b) {
   const uint64_t nrow = d->nrow, ncol = d->ncol;
-  const uint64_t cr = g.chunk_rows;
+  const bool pinned = is_pinned_host(data);
+  uint64_t cr = g.chunk_rows;
+  if (!pinned && cr > (1ull << 19)) cr = 1ull << 19;
   const size_t nchunk = (size_t)((nrow + cr - 1) / cr);
   float *X = d->X.p;
   const bool spec = b != nullptr;
@@ -309,43 +349,59 @@ void create_pipelined(DMatrix *d, const float *data, Booster *b) {
   }
   int *fl = g_chunk_flags.need(nchunk);
   int *hfl = g_h_chunk_flags.need(nchunk);
-  CU(cudaMemsetAsync(fl, 0, nchunk * sizeof(int), g.stream));
-  for (size_t c = 0; c < nchunk; ++c) {
-    const uint64_t r0 = c * cr, nr = std::min(cr, nrow - r0);
-    CU(cudaMemcpyAsync(X + r0 * ncol, data + r0 * ncol, nr * ncol * sizeof(float), cudaMemcpyHostToDevice, g.copy_stream));
-    CU(cudaEventRecord(chunk_event(3 * c), g.copy_stream));
-  }
+  CU(cudaMemsetAsync(fl, 0, nchunk * sizeof(int), g.copy_stream));
+  if (!pinned)
+    for (int s = 0; s < kStageSlots; ++s)
+      if (!g_stage_free[s]) CU(cudaEventCreateWithFlags(&g_stage_free[s], cudaEventDisableTiming));
   int flags = 0;
-  for (size_t c = 0; c < nchunk; ++c) {
+  auto issue = [&](size_t c) {
     const uint64_t r0 = c * cr, nr = std::min(cr, nrow - r0);
-    CU(cudaStreamWaitEvent(g.stream, chunk_event(3 * c), 0));
-    CU(launch_scan_matrix(X + r0 * ncol, nr * ncol, d->missing, fl + c, g.stream));
-    CU(cudaMemcpyAsync(hfl + c, fl + c, sizeof(int), cudaMemcpyDeviceToHost, g.stream));
-    CU(cudaEventRecord(chunk_event(3 * c + 1), g.stream));
-    CU(cudaEventSynchronize(chunk_event(3 * c + 1)));
+    const size_t bytes = nr * ncol * sizeof(float);
+    const float *src = data + r0 * ncol;
+    if (!pinned) {
+      const int s = (int)(c % kStageSlots);
+      float *st = g_stage[s].need(cr * ncol);
+      if (c >= (size_t)kStageSlots) CU(cudaEventSynchronize(g_stage_free[s]));  // its previous H2D has drained
+      parallel_memcpy(st, src, bytes);
+      src = st;
+      CU(cudaMemcpyAsync(X + r0 * ncol, src, bytes, cudaMemcpyHostToDevice, g.copy_stream));
+      CU(cudaEventRecord(g_stage_free[s], g.copy_stream));
+    } else {
+      CU(cudaMemcpyAsync(X + r0 * ncol, src, bytes, cudaMemcpyHostToDevice, g.copy_stream));
+    }
+    CU(launch_scan_matrix(X + r0 * ncol, nr * ncol, d->missing, fl + c, g.copy_stream));
+    CU(cudaMemcpyAsync(hfl + c, fl + c, sizeof(int), cudaMemcpyDeviceToHost, g.copy_stream));
+    CU(cudaEventRecord(chunk_event(2 * c), g.copy_stream));
+  };
+  auto process = [&](size_t c) {
+    const uint64_t r0 = c * cr, nr = std::min(cr, nrow - r0);
+    CU(cudaEventSynchronize(chunk_event(2 * c)));
     flags |= hfl[c];
     if (hfl[c] & 2) {
       drain();
       throw Error("Check failed: valid: Input data contains `inf` or `nan`");
     }
-    if (spec) {
-      PredictArgs a;
-      a.X = X + r0 * ncol, a.nrow = nr, a.ncol = (int32_t)ncol, a.missing = d->missing;
-      a.has_missing = ((hfl[c] & 1) || ncol < b->host.num_feature) ? 1 : 0;
-      a.ntree_used = (int32_t)b->host.trees.size();
-      a.out = sdev + r0;
-      CU(launch_predict(b->dev, a, g.tun, g.stream));
-      CU(cudaEventRecord(chunk_event(3 * c + 2), g.stream));
-      CU(cudaStreamWaitEvent(g.d2h_stream, chunk_event(3 * c + 2), 0));
-      CU(cudaMemcpyAsync(shost + r0, sdev + r0, nr * sizeof(float), cudaMemcpyDeviceToHost, g.d2h_stream));
-    }
+    if (!spec) return;
+    PredictArgs a;
+    a.X = X + r0 * ncol, a.nrow = nr, a.ncol = (int32_t)ncol, a.missing = d->missing;
+    a.has_missing = ((hfl[c] & 1) || ncol < b->host.num_feature) ? 1 : 0;
+    a.ntree_used = (int32_t)b->host.trees.size();
+    a.out = sdev + r0;
+    CU(launch_predict(b->dev, a, g.tun, g.stream));
+    CU(cudaEventRecord(chunk_event(2 * c + 1), g.stream));
+    CU(cudaStreamWaitEvent(g.d2h_stream, chunk_event(2 * c + 1), 0));
+    CU(cudaMemcpyAsync(shost + r0, sdev + r0, nr * sizeof(float), cudaMemcpyDeviceToHost, g.d2h_stream));
+  };
+  // pinned source: every copy can be queued up front; pageable: stage one chunk ahead of the GPU
+  const size_t lookahead = pinned ? nchunk : 1;
+  for (size_t c = 0; c < nchunk + lookahead; ++c) {
+    if (c < nchunk) issue(c);
+    if (c >= lookahead && c - lookahead < nchunk) process(c - lookahead);
   }
   CU(cudaStreamSynchronize(g.copy_stream));  // the borrowed host buffer has been read completely
   d->hflags = flags;
   d->sealed = true;
-  if (spec) {
-    d->spec_booster = b, d->spec_version = b->version, d->spec_ready = true;
-  }
+  if (spec) d->spec_booster = b, d->spec_version = b->version, d->spec_ready = true;
 }
 
 }  // namespace

@@ -14,10 +14,11 @@ b = capi.Booster(bench.booster_path())
 x = synth.quick_features(synth.raw_fields(a.grid))
 hx = capi.pinned_empty(x.shape); hx[:] = x
 print("rows", x.shape[0], "GB", x.nbytes / 1e9, flush=True)
-for spec, chunk in ((0, 0), (1, 0), (1, 1 << 19), (1, 1 << 23), (1, 0)):
+for spec, chunk, src, name in ((0, 0, hx, "pinned"), (1, 0, hx, "pinned"), (1, 1 << 19, hx, "pinned"), (0, 0, x, "pageable"), (1, 0, x, "pageable")):
     capi.set_param("speculate", spec); capi.set_param("chunk_rows", chunk)
+    print(name, flush=True)
     for it in range(a.iters):
-        t0 = time.perf_counter(); d = capi.DMatrix(hx); t1 = time.perf_counter()
+        t0 = time.perf_counter(); d = capi.DMatrix(src); t1 = time.perf_counter()
         n, p = b.predict_raw(d); t2 = time.perf_counter()
         d.free(); t3 = time.perf_counter()
         print(f"spec={spec} chunk={chunk} it={it}: create {1e3*(t1-t0):7.2f}  predict {1e3*(t2-t1):7.2f}  free {1e3*(t3-t2):6.2f}  total {1e3*(t3-t0):7.2f} ms", flush=True)
