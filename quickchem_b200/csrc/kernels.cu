@@ -135,9 +135,37 @@ __device__ __forceinline__ float export_transform(float acc, int exp10_on, float
   return __fmul_rn(p, scale);
 }
 
+// ---- TMA (bulk async copy) + mbarrier helpers: global -> shared without the LSU ------------------
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+
 template <int ILP, bool HAS_MISSING, bool PRED_LEAF, bool PARK, int MINB>
 __global__ void __launch_bounds__(kBlock, MINB) predict_rows_kernel(DeviceForest f, PredictArgs a) {
-  extern __shared__ float srow[];
+  extern __shared__ __align__(128) float srow[];
+  __shared__ __align__(8) unsigned long long tile_bar;
   const int tid = threadIdx.x;
   constexpr int B = kBlock;
   const uint64_t r0 = (uint64_t)blockIdx.x * B;
@@ -145,11 +173,26 @@ __global__ void __launch_bounds__(kBlock, MINB) predict_rows_kernel(DeviceForest
   const int nr = left < (uint64_t)B ? (int)left : B;
   const int ncol = a.ncol;
   {
-    // stage 1: coalesced copy of the tile's rows, row-major (the tile is one contiguous run of X)
+    // stage 1: the tile's rows are one contiguous run of X.  Full, 16-byte aligned tiles come in with a
+    // single bulk async copy (TMA, cp.async.bulk) completing on an mbarrier — no LSU instructions, no
+    // registers; the ragged tail tile (or a misaligned matrix) falls back to a coalesced LDG/STS loop.
     const float *__restrict__ src = a.X + r0 * (uint64_t)ncol;
     const int n = nr * ncol;
-    for (int i = tid; i < n; i += B) srow[i] = __ldg(src + i);
-    __syncthreads();
+    const uint32_t bytes = (uint32_t)n * 4u;
+    const bool bulk = ((bytes | (uint32_t)(uintptr_t)src) & 15u) == 0u;
+    if (bulk) {
+      const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&tile_bar);
+      if (tid == 0) mbar_init(bar, 1);
+      __syncthreads();
+      if (tid == 0) {
+        mbar_expect_tx(bar, bytes);
+        bulk_g2s((uint32_t)__cvta_generic_to_shared(srow), src, bytes, bar);
+      }
+      mbar_wait(bar, 0);
+    } else {
+      for (int i = tid; i < n; i += B) srow[i] = __ldg(src + i);
+      __syncthreads();
+    }
     // stage 2: each thread lifts its own row into registers (stride ncol: conflict-free for the
     // 27-column matrix), then writes it back transposed
     const float qnan = __int_as_float(0x7fc00000);
