@@ -233,6 +233,20 @@ void upload(Booster *b) {
   b->dev.max_depth = f.max_depth;
   b->dev.num_nodes = f.num_nodes();
   b->dev.base_score = b->host.base_score;
+  if (b->dev.tex) cudaDestroyTextureObject(b->dev.tex);
+  b->dev.tex = 0;
+  if (nn > 0 && nn < ((size_t)1 << 27)) {
+    cudaResourceDesc rd;
+    memset(&rd, 0, sizeof rd);
+    rd.resType = cudaResourceTypeLinear;
+    rd.res.linear.devPtr = b->d_nodes.p;
+    rd.res.linear.desc = cudaCreateChannelDesc<uint2>();
+    rd.res.linear.sizeInBytes = nn * 8;
+    cudaTextureDesc td;
+    memset(&td, 0, sizeof td);
+    td.readMode = cudaReadModeElementType;
+    CU(cudaCreateTextureObject(&b->dev.tex, &rd, &td, nullptr));
+  }
   b->uploaded = true;
 }
 

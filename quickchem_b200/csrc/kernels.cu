@@ -82,8 +82,10 @@ __device__ __forceinline__ uint32_t right_mask(float v, float thr) {
   return m;
 }
 
-template <int ILP, bool HAS_MISSING, bool PARK>
-__device__ __forceinline__ void walk_group(const uint2 *__restrict__ nodes, const uint32_t *__restrict__ toff,
+// TEXMODE is a bit mask over the ILP trees in flight: tree j fetches its nodes through the texture pipe
+// (tex1Dfetch on the same buffer) if bit j is set, through the LSU (LDG) otherwise.
+template <int ILP, bool HAS_MISSING, bool PARK, int TEXMODE = 0>
+__device__ __forceinline__ void walk_group(const uint2 *__restrict__ nodes, cudaTextureObject_t tex, const uint32_t *__restrict__ toff,
                                            const int32_t *__restrict__ tdepth, int t, uint32_t my_saddr,
                                            uint32_t (&idx)[ILP], uint32_t (&xbits)[ILP]) {
   int depth = 0;
@@ -105,7 +107,10 @@ __device__ __forceinline__ void walk_group(const uint2 *__restrict__ nodes, cons
 #pragma unroll
     for (int j = 0; j < ILP; ++j) {
       if (!PARK || rel[j] != 0u) {
-        nd[j] = __ldg(nodes + idx[j]);
+        if ((TEXMODE >> j) & 1)
+          nd[j] = tex1Dfetch<uint2>(tex, (int)idx[j]);
+        else
+          nd[j] = __ldg(nodes + idx[j]);
         // shared address of srow[feat][tid] = my_saddr + feat * (kBlock * 4): feat sits in the top byte
         // of the meta word, so the high half of meta * 2^(log2(kBlock*4) + 8) is feat * kBlock * 4; one
         // IMAD.WIDE with the thread's base address in the high word of the addend does it all
@@ -162,7 +167,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       : "memory");
 }
 
-template <int ILP, bool HAS_MISSING, bool PRED_LEAF, bool PARK, int MINB>
+template <int ILP, bool HAS_MISSING, bool PRED_LEAF, bool PARK, int MINB, int TEXMODE = 0>
 __global__ void __launch_bounds__(kBlock, MINB) predict_rows_kernel(DeviceForest f, PredictArgs a) {
   extern __shared__ __align__(128) float srow[];
   __shared__ __align__(8) unsigned long long tile_bar;
@@ -221,7 +226,7 @@ __global__ void __launch_bounds__(kBlock, MINB) predict_rows_kernel(DeviceForest
   int t = 0;
   for (; t + ILP <= ntree; t += ILP) {
     uint32_t idx[ILP], xb[ILP];
-    walk_group<ILP, HAS_MISSING, PARK>(f.nodes, f.tree_offset, f.tree_depth, t, my, idx, xb);
+    walk_group<ILP, HAS_MISSING, PARK, TEXMODE>(f.nodes, f.tex, f.tree_offset, f.tree_depth, t, my, idx, xb);
 #pragma unroll
     for (int j = 0; j < ILP; ++j) {
       if (PRED_LEAF) {
@@ -233,7 +238,7 @@ __global__ void __launch_bounds__(kBlock, MINB) predict_rows_kernel(DeviceForest
   }
   for (; t < ntree; ++t) {
     uint32_t idx[1], xb[1];
-    walk_group<1, HAS_MISSING, PARK>(f.nodes, f.tree_offset, f.tree_depth, t, my, idx, xb);
+    walk_group<1, HAS_MISSING, PARK, 0>(f.nodes, f.tex, f.tree_offset, f.tree_depth, t, my, idx, xb);
     if (PRED_LEAF) {
       if (live) a.out[row * (uint64_t)ntree + t] = (float)__ldg(f.orig_id + idx[0]);
     } else {
@@ -243,14 +248,14 @@ __global__ void __launch_bounds__(kBlock, MINB) predict_rows_kernel(DeviceForest
   if (!PRED_LEAF && live) a.out[row] = export_transform(acc, a.exp10, a.scale);
 }
 
-template <int ILP, bool HM, bool PL, bool PARK, int MINB>
+template <int ILP, bool HM, bool PL, bool PARK, int MINB, int TEXMODE = 0>
 static cudaError_t launch_predict_one(const DeviceForest &f, const PredictArgs &a, cudaStream_t s) {
   // srow holds max(ncol, nfeat + 1) feature slots per thread
   const int slots = (f.nfeat + 1) > a.ncol ? (f.nfeat + 1) : a.ncol;
   const size_t smem = (size_t)kBlock * slots * sizeof(float);
   const uint64_t nblk = (a.nrow + kBlock - 1) / kBlock;
   if (nblk > 0x7fffffffull) return cudaErrorInvalidConfiguration;
-  auto k = predict_rows_kernel<ILP, HM, PL, PARK, MINB>;
+  auto k = predict_rows_kernel<ILP, HM, PL, PARK, MINB, TEXMODE>;
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   k<<<dim3((unsigned)nblk), kBlock, smem, s>>>(f, a);
@@ -260,20 +265,41 @@ static cudaError_t launch_predict_one(const DeviceForest &f, const PredictArgs &
 cudaError_t launch_predict(const DeviceForest &f, const PredictArgs &a, const Tunables &t, cudaStream_t s) {
   if (a.nrow == 0) return cudaSuccess;
   if (a.ncol > 32 || f.nfeat > 31) return cudaErrorInvalidValue;  // staged through 32 registers (forest.hpp kMaxFeatures)
-  if (a.pred_leaf)
-    return a.has_missing ? launch_predict_one<4, true, true, true, 6>(f, a, s) : launch_predict_one<4, false, true, true, 6>(f, a, s);
-  if (a.has_missing) return launch_predict_one<4, true, false, true, 6>(f, a, s);
-  // clean matrix, sums: the production path; ILP / residency are tunable for experiments
-  if (t.park == 0) return launch_predict_one<4, false, false, false, 6>(f, a, s);
-  const int ilp = t.ilp > 0 ? t.ilp : 3, minb = t.minb > 0 ? t.minb : 6;
+  // Default build: 4 trees in flight per thread, trees 1 and 3 of each group fetch their nodes through
+  // the texture pipe, trees 0 and 2 through the LSU (mask 0xA).  The kernel is bound by the L1TEX
+  // data pipe; the two front ends have separate writeback paths, and splitting the gathers between
+  // them measured +10 % (profiles/README.md).  All-TEX is slower than all-LSU.
+  constexpr int kTex = 0xA;
+  const bool tex = f.tex != 0 && t.variant >= 0;
+  if (a.pred_leaf) {
+    if (a.has_missing)
+      return tex ? launch_predict_one<4, true, true, true, 6, kTex>(f, a, s) : launch_predict_one<4, true, true, true, 6, 0>(f, a, s);
+    return tex ? launch_predict_one<4, false, true, true, 6, kTex>(f, a, s) : launch_predict_one<4, false, true, true, 6, 0>(f, a, s);
+  }
+  if (a.has_missing)
+    return tex ? launch_predict_one<4, true, false, true, 6, kTex>(f, a, s) : launch_predict_one<4, true, false, true, 6, 0>(f, a, s);
+  // clean matrix, sums: the production path.  Experiments (qcoh_set_param): park, ilp, minb, variant.
+  if (t.park == 0) return launch_predict_one<4, false, false, false, 6, 0>(f, a, s);
+  if (t.variant > 0 && f.tex) {
+#define QC_TEX(V, I, MASK) \
+  if (t.variant == V) return launch_predict_one<I, false, false, true, 6, MASK>(f, a, s);
+    QC_TEX(1, 4, 0xF) QC_TEX(2, 4, 0xA) QC_TEX(3, 4, 0x8) QC_TEX(4, 4, 0xE)
+    QC_TEX(5, 3, 0x4) QC_TEX(6, 3, 0x6) QC_TEX(7, 6, 0x2A) QC_TEX(8, 6, 0x24) QC_TEX(9, 8, 0xAA)
+    QC_TEX(10, 2, 0x2) QC_TEX(11, 5, 0x0A) QC_TEX(12, 5, 0x15)
+#undef QC_TEX
+  }
+  if (t.ilp > 0 || t.minb > 0 || !tex) {  // LSU-only builds
+    const int ilp = t.ilp > 0 ? t.ilp : 3, minb = t.minb > 0 ? t.minb : 6;
 #define QC_CASE(I, M) \
-  if (ilp == I && minb == M) return launch_predict_one<I, false, false, true, M>(f, a, s);
-  QC_CASE(1, 6) QC_CASE(2, 6) QC_CASE(3, 6) QC_CASE(4, 6) QC_CASE(6, 6)
-  QC_CASE(2, 5) QC_CASE(3, 5) QC_CASE(4, 5) QC_CASE(6, 5)
-  QC_CASE(2, 4) QC_CASE(3, 4) QC_CASE(4, 4) QC_CASE(6, 4) QC_CASE(8, 4)
-  QC_CASE(4, 3) QC_CASE(6, 3) QC_CASE(8, 3)
+  if (ilp == I && minb == M) return launch_predict_one<I, false, false, true, M, 0>(f, a, s);
+    QC_CASE(1, 6) QC_CASE(2, 6) QC_CASE(3, 6) QC_CASE(4, 6) QC_CASE(6, 6)
+    QC_CASE(2, 5) QC_CASE(3, 5) QC_CASE(4, 5) QC_CASE(6, 5)
+    QC_CASE(2, 4) QC_CASE(3, 4) QC_CASE(4, 4) QC_CASE(6, 4) QC_CASE(8, 4)
+    QC_CASE(4, 3) QC_CASE(6, 3) QC_CASE(8, 3)
 #undef QC_CASE
-  return launch_predict_one<4, false, false, true, 6>(f, a, s);
+    return launch_predict_one<3, false, false, true, 6, 0>(f, a, s);
+  }
+  return launch_predict_one<4, false, false, true, 6, kTex>(f, a, s);
 }
 
 // =====================================================================================

@@ -12,6 +12,7 @@ struct DeviceForest {
   const uint32_t *tree_offset = nullptr; // [ntree + 1]
   const int32_t *tree_depth = nullptr;   // [ntree]
   const int32_t *orig_id = nullptr;      // [num_nodes]
+  cudaTextureObject_t tex = 0;           // the same nodes as a 1-D linear uint2 texture (TEX pipe)
   int32_t ntree = 0;
   int32_t nfeat = 0;
   int32_t max_depth = 0;

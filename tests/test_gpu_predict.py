@@ -210,10 +210,17 @@ def test_kernel_variants_agree(capi, oracle, small_model_path, small_forest):
                     capi.set_param("ilp", ilp)
                     capi.set_param("minb", minb)
                     assert np.array_equal(b.predict(d).view(np.uint32), ref.view(np.uint32)), (park, ilp, minb)
+        capi.set_param("ilp", 0)
+        capi.set_param("minb", 0)
+        capi.set_param("park", -1)
+        for variant in (-1, 0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12):  # LSU / texture-pipe mixes
+            capi.set_param("variant", variant)
+            assert np.array_equal(b.predict(d).view(np.uint32), ref.view(np.uint32)), variant
     finally:
         capi.set_param("ilp", 0)
         capi.set_param("minb", 0)
         capi.set_param("park", -1)
+        capi.set_param("variant", 0)
 
 
 def test_pipelined_create_matches_plain_path(capi, oracle, tmp_path, small_model_path, small_forest):
