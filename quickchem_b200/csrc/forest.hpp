@@ -37,11 +37,12 @@ struct HostForest {
 // Flattened layout (see DESIGN.md "Node layout").  Per tree the nodes are renumbered in
 // breadth-first (depth) order, siblings adjacent (right = left + 1).  One node = 8 bytes:
 //   x: float bits — split threshold, or the leaf value at a leaf
-//   y: meta = feat << 24 | default_left << 23 | rel   (rel = left-child index - own index)
+//   y: meta = feat << 26 | default_left << 23 | rel   (rel = left-child index - own index; the top byte is
+//      feat * 4, so one byte-permute turns it into the byte offset feat * 1024 of the kernel's feature tile)
 // A leaf has rel = 0 and feat = num_feature: the predict kernel keeps one extra per-row
 // slot holding -inf at that feature index, so `!(v < x)` is false and the walk self-loops
 // without a leaf test.
-constexpr uint32_t kMetaFeatShift = 24;
+constexpr uint32_t kMetaFeatShift = 26;
 constexpr uint32_t kMetaDefaultLeftBit = 1u << 23;
 constexpr uint32_t kMetaRelMask = (1u << 23) - 1;
 constexpr uint32_t kMaxFeatures = 31;  // the predict kernel stages a row through 32 registers

@@ -111,12 +111,10 @@ __device__ __forceinline__ void walk_group(const uint2 *__restrict__ nodes, cuda
           nd[j] = tex1Dfetch<uint2>(tex, (int)idx[j]);
         else
           nd[j] = __ldg(nodes + idx[j]);
-        // shared address of srow[feat][tid] = my_saddr + feat * (kBlock * 4): feat sits in the top byte
-        // of the meta word, so the high half of meta * 2^(log2(kBlock*4) + 8) is feat * kBlock * 4; one
-        // IMAD.WIDE with the thread's base address in the high word of the addend does it all
-        static_assert(kBlock * 4 == 1024 && kMetaFeatShift == 24, "address trick assumes 1 KB feature stride");
-        const uint64_t prod = (uint64_t)(nd[j].y & 0xFF000000u) * 1024u * 256u + ((uint64_t)my_saddr << 32);
-        const uint32_t sa = (uint32_t)(prod >> 32);
+        // shared address of srow[feat][tid] = my_saddr + feat * (kBlock * 4): the top byte of the meta word
+        // is feat * 4, so moving it to byte 1 (one PRMT) gives feat * 1024
+        static_assert(kBlock * 4 == 1024 && kMetaFeatShift == 26, "address trick assumes a 1 KB feature stride");
+        const uint32_t sa = my_saddr + __byte_perm(nd[j].y, 0u, 0x4434);
         float v;
         asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(sa));
         uint32_t m = right_mask(v, __uint_as_float(nd[j].x));
@@ -126,6 +124,8 @@ __device__ __forceinline__ void walk_group(const uint2 *__restrict__ nodes, cuda
         rel[j] = nd[j].y & kMetaRelMask;
         idx[j] = idx[j] + rel[j] - m;
       }
+      // keep "still walking" in the rel register only (one ISETP per level instead of predicate shuffling)
+      if (PARK) asm volatile("" : "+r"(rel[j]));
     }
   }
 #pragma unroll

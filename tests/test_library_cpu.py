@@ -40,7 +40,7 @@ def _flat_walk(nodes, off, orig, t, row, nfeat):
     while True:
         x, meta = nodes[i]
         rel = int(meta) & ((1 << 23) - 1)
-        feat = int(meta) >> 24
+        feat = int(meta) >> 26
         if rel == 0:
             assert feat == nfeat
             return int(orig[i]), np.array([x], np.uint32).view(np.float32)[0]
@@ -94,7 +94,7 @@ def test_flat_layout_is_depth_ordered(capi, tmp_path):
         # children adjacent: right = left + 1
         assert np.array_equal(ids[(pos + rel)[internal]], tree.left[ids[internal]])
         assert np.array_equal(ids[(pos + rel + 1)[internal]], tree.right[ids[internal]])
-        assert np.array_equal(meta[internal] >> 24, tree.split_index[ids[internal]])
+        assert np.array_equal(meta[internal] >> 26, tree.split_index[ids[internal]])
         assert np.array_equal((meta[internal] >> 23) & 1, tree.default_left[ids[internal]])
         assert np.array_equal(nodes[n0:n1, 0].view(np.float32), tree.split_cond[ids])
 

@@ -25,11 +25,11 @@ a = ap.parse_args()
 for kv in a.param:
     k, v = kv.split("=")
     capi.set_param(k, v)
-b = capi.Booster(a.model or bench.booster_path())
 x = synth.quick_features(synth.raw_fields(a.grid, rho=a.rho))
 if a.shuffle:
     x = x[np.random.default_rng(0).permutation(x.shape[0])]
-d = capi.DMatrix(x)
+d = capi.DMatrix(x)  # before any booster exists: no pipelined prediction, only full-size launches below
+b = capi.Booster(a.model or bench.booster_path())
 out = capi.DeviceArray(x.shape[0])
 
 
