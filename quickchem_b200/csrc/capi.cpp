@@ -223,7 +223,23 @@ void upload(Booster *b) {
   ensure_device();
   const FlatForest &f = b->flat;
   const size_t nn = (size_t)f.num_nodes();
-  CU(cudaMemcpy(b->d_nodes.need(nn), f.nodes_xy.data(), nn * 8, cudaMemcpyHostToDevice));
+  {
+    // device copy: an internal node's x word becomes -key(threshold) mod 2^32 (kernels.cu "Order-
+    // preserving integer keys"); leaves keep the float bits of their value
+    std::vector<uint32_t> dev_nodes(f.nodes_xy);
+    for (size_t i = 0; i < nn; ++i) {
+      if ((dev_nodes[2 * i + 1] & kMetaRelMask) == 0) continue;
+      float thr;
+      memcpy(&thr, &dev_nodes[2 * i], 4);
+      if (std::isnan(thr)) throw Error("split threshold is NaN (node " + std::to_string(i) + ")");
+      thr += 0.0f;  // -0.0 -> +0.0
+      uint32_t bits;
+      memcpy(&bits, &thr, 4);
+      const uint32_t key = bits ^ ((bits >> 31) ? 0xFFFFFFFFu : 0x80000000u);
+      dev_nodes[2 * i] = 0u - key;  // key >= 0x007FFFFF (-inf), never 0
+    }
+    CU(cudaMemcpy(b->d_nodes.need(nn), dev_nodes.data(), nn * 8, cudaMemcpyHostToDevice));
+  }
   CU(cudaMemcpy(b->d_off.need(f.tree_offset.size()), f.tree_offset.data(), f.tree_offset.size() * 4, cudaMemcpyHostToDevice));
   CU(cudaMemcpy(b->d_depth.need(f.tree_depth.size()), f.tree_depth.data(), f.tree_depth.size() * 4, cudaMemcpyHostToDevice));
   CU(cudaMemcpy(b->d_orig.need(nn), f.orig_id.data(), nn * 4, cudaMemcpyHostToDevice));

@@ -75,11 +75,23 @@ cudaError_t launch_fill(float *p, uint64_t n, float v, cudaStream_t s) {
 // left + !(fvalue < split_cond); out = base_score, then += leaf value tree by tree in float32.
 constexpr int kBlock = 256;  // rows per CTA; the feature stride in the transposed tile is kBlock floats
 
-// 0xFFFFFFFF if !(v < thr) (i.e. v >= thr or unordered), else 0 — one FSET, no predicate register
-__device__ __forceinline__ uint32_t right_mask(float v, float thr) {
-  uint32_t m;
-  asm("set.geu.u32.f32 %0, %1, %2;" : "=r"(m) : "f"(v), "f"(thr));
-  return m;
+// Order-preserving integer keys.  The tile and the device copy of the nodes do not hold floats but
+// key(v) = bits ^ (sign ? 0xFFFFFFFF : 0x80000000) of the value with -0.0 folded into +0.0, which is
+// monotone: a < b  <=>  key(a) < key(b) (unsigned) for all non-NaN floats, and key(-0) == key(+0) like
+// the float compare.  An internal node stores x = -key(threshold) (mod 2^32; key(thr) is never 0), so
+//     !(v < thr)  <=>  key(thr) <= key(v)  <=>  x + key(v) >= 2^32
+// which is the carry of x + key(v): `add.cc` + `addc` fold the compare into the index update
+// (idx += rel + right) in two instructions and no predicate.  Missing is key 0xFFFFFFFF (above +inf).
+// The per-row slot `nfeat` that leaves point at holds key 0: nothing carries, the walk self-loops.
+constexpr uint32_t kKeyMissing = 0xFFFFFFFFu;
+__device__ __forceinline__ uint32_t float_key(float v) {
+  const uint32_t b = __float_as_uint(__fadd_rn(v, 0.0f));  // -0.0 + 0.0 = +0.0
+  return b ^ ((uint32_t)((int32_t)b >> 31) | 0x80000000u);
+}
+// idx + rel + carry(x + kv)
+__device__ __forceinline__ uint32_t step_index(uint32_t idx, uint32_t rel, uint32_t x, uint32_t kv) {
+  asm("{\n\t.reg .u32 t;\n\tadd.cc.u32 t, %2, %3;\n\taddc.u32 %0, %0, %1;\n\t}" : "+r"(idx) : "r"(rel), "r"(x), "r"(kv));
+  return idx;
 }
 
 // TEXMODE is a bit mask over the ILP trees in flight: tree j fetches its nodes through the texture pipe
@@ -115,14 +127,13 @@ __device__ __forceinline__ void walk_group(const uint2 *__restrict__ nodes, cuda
         // is feat * 4, so moving it to byte 1 (one PRMT) gives feat * 1024
         static_assert(kBlock * 4 == 1024 && kMetaFeatShift == 26, "address trick assumes a 1 KB feature stride");
         const uint32_t sa = my_saddr + __byte_perm(nd[j].y, 0u, 0x4434);
-        float v;
-        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(sa));
-        uint32_t m = right_mask(v, __uint_as_float(nd[j].x));
-        if (HAS_MISSING) {
-          if (v != v) m = (nd[j].y & kMetaDefaultLeftBit) ? 0u : 0xFFFFFFFFu;
-        }
+        uint32_t kv;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(kv) : "r"(sa));
         rel[j] = nd[j].y & kMetaRelMask;
-        idx[j] = idx[j] + rel[j] - m;
+        if (HAS_MISSING && kv == kKeyMissing)  // default child: left = idx + rel, right = left + 1
+          idx[j] += rel[j] + ((nd[j].y & kMetaDefaultLeftBit) ? 0u : (rel[j] != 0u ? 1u : 0u));
+        else
+          idx[j] = step_index(idx[j], rel[j], nd[j].x, kv);
       }
       // keep "still walking" in the rel register only (one ISETP per level instead of predicate shuffling)
       if (PARK) asm volatile("" : "+r"(rel[j]));
@@ -170,6 +181,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 template <int ILP, bool HAS_MISSING, bool PRED_LEAF, bool PARK, int MINB, int TEXMODE = 0>
 __global__ void __launch_bounds__(kBlock, MINB) predict_rows_kernel(DeviceForest f, PredictArgs a) {
   extern __shared__ __align__(128) float srow[];
+  uint32_t *skey = reinterpret_cast<uint32_t *>(srow);  // the transposed tile holds keys, not floats
   __shared__ __align__(8) unsigned long long tile_bar;
   const int tid = threadIdx.x;
   constexpr int B = kBlock;
@@ -200,7 +212,6 @@ __global__ void __launch_bounds__(kBlock, MINB) predict_rows_kernel(DeviceForest
     }
     // stage 2: each thread lifts its own row into registers (stride ncol: conflict-free for the
     // 27-column matrix), then writes it back transposed
-    const float qnan = __int_as_float(0x7fc00000);
     float v[32];
     const int nc32 = ncol < 32 ? ncol : 32;
 #pragma unroll
@@ -209,13 +220,14 @@ __global__ void __launch_bounds__(kBlock, MINB) predict_rows_kernel(DeviceForest
 #pragma unroll
     for (int c = 0; c < 32; ++c)
       if (c < nc32) {
-        float x = v[c];
-        if (HAS_MISSING && x == a.missing) x = qnan;
-        srow[c * B + tid] = x;
+        const float x = v[c];
+        uint32_t k = float_key(x);
+        if (HAS_MISSING && (x != x || x == a.missing)) k = kKeyMissing;
+        skey[c * B + tid] = k;
       }
     // columns the matrix does not have are missing (xgboost FVec::Fill leaves them flagged)
-    for (int c = nc32; c < f.nfeat; ++c) srow[c * B + tid] = qnan;
-    srow[f.nfeat * B + tid] = -INFINITY;
+    for (int c = nc32; c < f.nfeat; ++c) skey[c * B + tid] = kKeyMissing;
+    skey[f.nfeat * B + tid] = 0u;
   }
   if (tid >= nr) return;
   const bool live = true;
