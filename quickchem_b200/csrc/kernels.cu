@@ -298,6 +298,9 @@ cudaError_t launch_predict(const DeviceForest &f, const PredictArgs &a, const Tu
     QC_TEX(1, 4, 0xF) QC_TEX(2, 4, 0xA) QC_TEX(3, 4, 0x8) QC_TEX(4, 4, 0xE)
     QC_TEX(5, 3, 0x4) QC_TEX(6, 3, 0x6) QC_TEX(7, 6, 0x2A) QC_TEX(8, 6, 0x24) QC_TEX(9, 8, 0xAA)
     QC_TEX(10, 2, 0x2) QC_TEX(11, 5, 0x0A) QC_TEX(12, 5, 0x15)
+    QC_TEX(13, 6, 0x36) QC_TEX(14, 5, 0x1E) QC_TEX(15, 8, 0xEE) QC_TEX(16, 6, 0x3E) QC_TEX(17, 7, 0x5A) QC_TEX(18, 7, 0x6D)
+    if (t.variant == 20) return launch_predict_one<4, false, false, true, 5, 0xA>(f, a, s);
+    if (t.variant == 21) return launch_predict_one<4, false, false, true, 4, 0xA>(f, a, s);
 #undef QC_TEX
   }
   if (t.ilp > 0 || t.minb > 0 || !tex) {  // LSU-only builds
