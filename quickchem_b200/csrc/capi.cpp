@@ -860,7 +860,7 @@ struct Oh {
   // resident copies of host-provided inputs, one slot per input field
   static constexpr int kNumIn = 13 + 7 + 11 + 5 + 1 + 1;
   DevBuf<float> in[kNumIn];
-  DevBuf<float> PL_MOD, NDWET, sums[6], OH_ML, OH, OH_boost, X, pred, sza;
+  DevBuf<float> PL_MOD, NDWET, sums[6], OH_ML, OH, OH_boost, X, pred, sza, lat_deg, so3;
   DevBuf<int> ctl;
   DevBuf<double> diag;
   PinBuf<float> h_sza, h_lat, h_lon;
@@ -995,6 +995,7 @@ int qcoh_oh_run1(qcoh_oh_handle h, const qcoh_run1_in *in, qcoh_run1_out *out) {
   CU(cudaMemsetAsync(r.ctl, 0, 4 * sizeof(int), g.stream));
   CU(launch_oh_state(r, g.stream));
   out->k1 = 0;
+  bool check_inf_after = false;
   if (boost) {
     int ctl[4];
     CU(cudaMemcpyAsync(ctl, r.ctl, sizeof ctl, cudaMemcpyDeviceToHost, g.stream));
@@ -1005,13 +1006,31 @@ int qcoh_oh_run1(qcoh_oh_handle h, const qcoh_run1_in *in, qcoh_run1_out *out) {
     out->k1 = k1;
     const uint64_t npred = (uint64_t)nc * ksub;
     for (int i = 0; i < 6; ++i) r.sums[i] = o->sums[i].need(n3);
+    r.lat_deg = o->lat_deg.need(n2), r.so3 = o->so3.need(n2);
     CU(launch_oh_sums(r, g.stream));
     CU(cudaMemsetAsync(r.OH_ML, 0, n3 * 4, g.stream));  // self%OH_ML = 0.0 (:1559)
-    if (npred) {
+    if (npred && !out->X) {
+      // fused: pack (:303-345) + create (:347) + predict (:356) + 10**x (:369) * OHscale (:1569) in one
+      // kernel reading the SoA fields; the [N x 27] matrix is never formed
+      SoaArgs a;
+      const float *s3[27] = {nullptr, nullptr, r.T_BST, r.NO2, r.O3, r.CH4, r.CO, r.ISOP, r.ACET, r.C2H6, r.C3H8, r.PRPE,
+                             r.ALK4, r.MP, r.H2O2, r.sums[0], r.sums[1], r.sums[2], r.sums[3], r.FCLD, r.Q_BST, nullptr,
+                             nullptr, r.sums[4], r.sums[5], r.CH2O, nullptr};
+      const float *s2[27] = {nullptr};
+      s2[0] = r.lat_deg, s2[21] = r.so3, s2[22] = r.ALBUV, s2[26] = r.SZA;
+      for (int f = 0; f < 27; ++f) a.src3[f] = s3[f], a.src2[f] = s2[f];
+      a.ple = r.PLE_BST, a.ncol = nc, a.e0 = (uint64_t)(k1 - 1) * nc, a.nrow = npred, a.missing = c.missing;
+      a.ntree_used = o->booster->dev.ntree, a.exp10 = 1, a.scale = c.ohscale;
+      a.out = r.OH_ML + (size_t)(k1 - 1) * nc;
+      a.pred = out->pred ? o->pred.need(npred) : nullptr;
+      a.flags = r.ctl + 2;
+      CU(launch_predict_soa(o->booster->dev, a, g.tun, g.stream));
+      if (out->pred) deliver(out->pred, a.pred, npred);
+      check_inf_after = true;
+    } else if (npred) {
+      // debug / parity path: materialise xx_carr so that it can be handed back (out->X)
       float *X = o->X.need(npred * 27);
       CU(launch_oh_pack(r, k1, X, g.stream));
-      // xx_carr -> XGDMatrixCreateFromMat -> XGBoosterPredict -> 10**x (:347-374) and * OHscale
-      // (:1569), without leaving HBM: the predict kernel's epilogue writes OH_ML's slab in place
       int flags = 0;
       CU(cudaMemcpyAsync(&flags, r.ctl + 2, sizeof(int), cudaMemcpyDeviceToHost, g.stream));
       CU(cudaStreamSynchronize(g.stream));
@@ -1039,7 +1058,13 @@ int qcoh_oh_run1(qcoh_oh_handle h, const qcoh_run1_in *in, qcoh_run1_out *out) {
   deliver(out->OH, r.OH, n3);
   deliver(out->OH_boost, r.OH_boost, n3);
   deliver(out->NDWET, r.NDWET, n3);
+  int inf_flags = 0;
+  if (check_inf_after) CU(cudaMemcpyAsync(&inf_flags, r.ctl + 2, sizeof(int), cudaMemcpyDeviceToHost, g.stream));
   CU(cudaStreamSynchronize(g.stream));
+  if ((inf_flags & 2) && !std::isinf(c.missing)) {
+    o->oh_ml_valid = false;
+    throw Error("Check failed: valid: Input data contains `inf` or `nan`");
+  }
   API_END
 }
 

@@ -260,6 +260,90 @@ __global__ void __launch_bounds__(kBlock, MINB) predict_rows_kernel(DeviceForest
   if (!PRED_LEAF && live) a.out[row] = export_transform(acc, a.exp10, a.scale);
 }
 
+// ---- fused Run1 variant: the tile is assembled straight from the SoA feature fields ------------------
+// (OH_GridCompMod.F90:303-345 pack + :347 create + :356 predict + :369,:1569 transform in one kernel).
+// Row m of the slab is cell e = e0 + m; per feature the CTA's 256 cells are contiguous in the source
+// field, so every load is coalesced and lands directly in the transposed tile — the [N x 27] matrix is
+// never formed, and no transposition is needed.  Whether a tile holds missing entries is decided per
+// tile (block-wide OR) and selects the walk specialisation at run time; +-inf raises the error flag.
+template <int ILP, bool HAS_MISSING, bool PARK, int TEXMODE>
+__device__ __forceinline__ float forest_sum(const DeviceForest &f, uint32_t my, int ntree) {
+  float acc = f.base_score;
+  int t = 0;
+  for (; t + ILP <= ntree; t += ILP) {
+    uint32_t idx[ILP], xb[ILP];
+    walk_group<ILP, HAS_MISSING, PARK, TEXMODE>(f.nodes, f.tex, f.tree_offset, f.tree_depth, t, my, idx, xb);
+#pragma unroll
+    for (int j = 0; j < ILP; ++j) acc = __fadd_rn(acc, __uint_as_float(xb[j]));
+  }
+  for (; t < ntree; ++t) {
+    uint32_t idx[1], xb[1];
+    walk_group<1, HAS_MISSING, PARK, 0>(f.nodes, f.tex, f.tree_offset, f.tree_depth, t, my, idx, xb);
+    acc = __fadd_rn(acc, __uint_as_float(xb[0]));
+  }
+  return acc;
+}
+
+template <int TEXMODE>
+__global__ void __launch_bounds__(kBlock, 6) predict_soa_kernel(DeviceForest f, SoaArgs a) {
+  extern __shared__ __align__(128) float srow[];
+  uint32_t *skey = reinterpret_cast<uint32_t *>(srow);
+  const int tid = threadIdx.x;
+  constexpr int B = kBlock;
+  const uint64_t m = (uint64_t)blockIdx.x * B + tid;
+  const bool live = m < a.nrow;
+  int flags = 0;
+  if (live) {
+    const size_t e = a.e0 + m;
+    const int c = (int)(m % (uint64_t)a.ncol);
+    const bool chk_inf = !isinf(a.missing);
+#pragma unroll
+    for (int ft = 0; ft < 27; ++ft) {
+      float x;
+      if (ft == 1)  // PL_BST = (PLE(k-1) + PLE(k)) * 0.5 (:1488), / 100.0 as a true divide (:314)
+        x = __fdiv_rn(__fmul_rn(__fadd_rn(__ldg(a.ple + e), __ldg(a.ple + e + a.ncol)), 0.5f), 100.0f);
+      else
+        x = a.src3[ft] ? __ldg(a.src3[ft] + e) : __ldg(a.src2[ft] + c);
+      uint32_t k = float_key(x);
+      if (x != x || x == a.missing) k = kKeyMissing, flags |= 1;
+      if (chk_inf && isinf(x)) flags |= 2;
+      skey[ft * B + tid] = k;
+    }
+  } else {
+#pragma unroll
+    for (int ft = 0; ft < 27; ++ft) skey[ft * B + tid] = 0u;
+  }
+  skey[27 * B + tid] = 0u;  // the slot leaves point at (nfeat == 27 is checked by the host)
+  // __syncthreads_or returns a truth value, not the bitwise OR: one vote per flag
+  const bool tile_missing = __syncthreads_or(flags & 1) != 0;
+  if (__syncthreads_or(flags & 2) != 0) {
+    if (tid == 0) atomicOr(a.flags, 2);
+  }
+  if (!live) return;
+  const uint32_t my = (uint32_t)__cvta_generic_to_shared(srow + tid);
+  float acc;
+  if (tile_missing)
+    acc = forest_sum<4, true, true, TEXMODE>(f, my, a.ntree_used);
+  else
+    acc = forest_sum<4, false, true, TEXMODE>(f, my, a.ntree_used);
+  if (a.pred) a.pred[m] = acc;
+  a.out[m] = export_transform(acc, a.exp10, a.scale);
+}
+
+cudaError_t launch_predict_soa(const DeviceForest &f, const SoaArgs &a, const Tunables &t, cudaStream_t s) {
+  if (a.nrow == 0) return cudaSuccess;
+  if (f.nfeat != 27) return cudaErrorInvalidValue;
+  const size_t smem = (size_t)kBlock * 28 * sizeof(float);
+  const uint64_t nblk = (a.nrow + kBlock - 1) / kBlock;
+  if (nblk > 0x7fffffffull) return cudaErrorInvalidConfiguration;
+  const bool tex = f.tex != 0 && t.variant >= 0;
+  auto k = tex ? predict_soa_kernel<0xA> : predict_soa_kernel<0>;
+  cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  k<<<dim3((unsigned)nblk), kBlock, smem, s>>>(f, a);
+  return QC_LAUNCHED();
+}
+
 template <int ILP, bool HM, bool PL, bool PARK, int MINB, int TEXMODE = 0>
 static cudaError_t launch_predict_one(const DeviceForest &f, const PredictArgs &a, cudaStream_t s) {
   // srow holds max(ncol, nfeat + 1) feature slots per thread
@@ -369,6 +453,8 @@ __global__ void __launch_bounds__(128) oh_sums_kernel(Run1Dev r, float *__restri
   if (c >= r.ncol) return;
   const int nc = r.ncol, km = r.km;
   float *wdn = r.sums[0], *idn = r.sums[1], *iup = r.sums[2], *wup = r.sums[3], *aup = r.sums[4], *adn = r.sums[5];
+  if (r.lat_deg) r.lat_deg[c] = __fmul_rn(r.LATS[c], r.r2d);         // latarr (:1444)
+  if (r.so3) r.so3[c] = __fadd_rn(r.GMITO3[c], -r.GMITTO3[c]);       // stratO3 (:1446)
   // pass 1: aod and the UP prefixes
   float s_iup = 0.f, s_wup = 0.f, s_aup = 0.f;
   float z_up = r.ZLE_BST[c];

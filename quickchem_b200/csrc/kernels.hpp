@@ -50,6 +50,24 @@ cudaError_t launch_scan_matrix(const float *X, uint64_t n, float missing, int *f
 
 cudaError_t launch_predict(const DeviceForest &f, const PredictArgs &a, const Tunables &t, cudaStream_t s);
 
+// Fused Run1 predict: features come straight from the SoA fields (27 sources in feature order)
+struct SoaArgs {
+  const float *src3[27];     // [km][ncol] source of feature f, or nullptr if it is a 2-D field
+  const float *src2[27];     // [ncol] source of a 2-D feature
+  const float *ple = nullptr;  // PLE_BST [km+1][ncol] (feature 1 is computed from it)
+  int32_t ncol = 0;
+  uint64_t e0 = 0;           // cell index of slab row 0: (k1 - 1) * ncol
+  uint64_t nrow = 0;         // ncol * ksub
+  float missing = -999.f;
+  int32_t ntree_used = 0;
+  int exp10 = 1;
+  float scale = 1.f;
+  float *out = nullptr;      // OH_ML slab
+  float *pred = nullptr;     // optional raw booster output
+  int *flags = nullptr;      // |= 2 on +-inf input
+};
+cudaError_t launch_predict_soa(const DeviceForest &f, const SoaArgs &a, const Tunables &t, cudaStream_t s);
+
 // ---- fused Run1 pieces (OH_GridCompMod.F90:1232-1599) ---------------------------------
 struct Run1Dev {
   int32_t ncol = 0, km = 0;
@@ -68,6 +86,7 @@ struct Run1Dev {
   // work / outputs (device)
   float *PL_MOD, *NDWET;             // [km][ncol]
   float *sums[6];                    // wdn idn iup wup aup adn, [km][ncol]
+  float *lat_deg, *so3;              // [ncol] latarr, stratO3 (written by oh_sums)
   float *OH_ML;                      // persistent [km][ncol]
   float *OH, *OH_boost;              // [km][ncol]
   int *ctl;                          // [0] ksub (atomicMax) [1] tropp<=tropp_min count [2] matrix flags

@@ -54,6 +54,35 @@ def test_run1_once_per_day(capi, oracle, small_model_path, n):
     assert np.all(got["OH_boost"][: got["k1"] - 1] == 0)
 
 
+def test_run1_fused_path_equals_matrix_path(capi, oracle, small_model_path):
+    """Without `X` in the request qcoh_oh_run1 never forms the [N x 27] matrix (predict_soa_kernel reads the
+    SoA fields); the outputs must be the very same bits as the matrix path, with and without missing data."""
+    for poke in (False, True):
+        fields = dict(synth.raw_fields(8))
+        if poke:
+            for name, where in (("oh_NO2", (40, 7)), ("T", (60, 100)), ("oh_ALBUV", (33,))):
+                fields[name] = fields[name].copy()
+                fields[name][where] = -999.0
+            fields["CO"] = fields["CO"].copy()
+            fields["CO"][50, 3] = np.nan
+        km, ncol = fields["T"].shape
+        oh = capi.OhRun1(capi.Booster(small_model_path), ncol, km, synth.MAPL)
+        a = oh.run(oh.make_in(fields), want=("OH", "OH_boost", "X", "pred"))
+        b = oh.run(oh.make_in(fields), want=("OH", "OH_boost", "pred"))
+        c = oh.run(oh.make_in(fields), want=("OH", "OH_boost"))
+        ref = oracle.run1(oracle.Model(small_model_path), fields, synth.MAPL, want_features=True)
+        assert np.array_equal(a["pred"].view(np.uint32), ref["pred"].view(np.uint32))
+        for k in ("OH", "OH_boost", "pred"):
+            assert np.array_equal(a[k].view(np.uint32), b[k].view(np.uint32)), (poke, k)
+        assert np.array_equal(a["OH"].view(np.uint32), c["OH"].view(np.uint32))
+    fields["oh_O3"] = fields["oh_O3"].copy()
+    fields["oh_O3"][70, 5] = np.inf
+    with pytest.raises(capi.QcohError, match="inf"):
+        oh.run(oh.make_in(fields), want=("OH",))
+    with pytest.raises(capi.QcohError, match="inf"):
+        oh.run(oh.make_in(fields), want=("OH", "X"))
+
+
 def test_run1_dynamic_k_range(capi, oracle, small_model_path):
     fields = synth.raw_fields(8)
     got, ref, _, _ = _run_both(capi, oracle, small_model_path, fields, compute_once_per_day=False, nymd=20240229)
