@@ -66,5 +66,12 @@
 !   rc = qcoh_oh_run1( oh_dev, rin, rout )
 !   _ASSERT(rc==0, qcoh_last_error())      ! carries 'Minimum tropopause pressure is not low enough!' (:288)
 !
+!   AFTER_BOOST: IF ( need_to_call_BOOST ) THEN      ! diagnostics (:1602-1728) straight from HBM
+!      CALL MAPL_GetPointer(export, ptr3d, 'DIAG_AODUP', __RC__)
+!      IF (ASSOCIATED(ptr3d)) rc = qcoh_oh_get_diag( oh_dev, 'AODUP'//c_null_char, c_loc(ptr3d) )
+!      ...  TAUCLWDN TAUCLIDN TAUCLIUP TAUCLWUP AODDN PL NDWET OH_boost (3-D), LAT SZA stratO3 (2-D);
+!      the remaining DIAG_* exports are plain copies of import fields and stay in Fortran
+!   END IF AFTER_BOOST
+!
 ! The persistent self%OH_ML(:,:,:) (:76-78,:893) lives in HBM inside oh_dev; with
 ! compute_once_per_day the 23 non-boost steps of a day upload only T, Q, PLE, TROPP and oh_OH.

@@ -65,6 +65,14 @@ module qcoh_fortran_api
        type(qcoh_run1_out) :: rout
      end function
 
+     ! DIAG_* exports: name = "TAUCLWDN"//c_null_char etc. (include/qcoh.h)
+     integer(c_int) function qcoh_oh_get_diag(h, name, out) bind(C, name="qcoh_oh_get_diag")
+       import :: c_int, c_ptr, c_char
+       type(c_ptr), value :: h
+       character(len=1, kind=c_char), dimension(*) :: name
+       type(c_ptr), value :: out   ! c_loc of the export array (host) or a device pointer
+     end function
+
      integer(c_int) function qcoh_oh_free(h) bind(C, name="qcoh_oh_free")
        import :: c_int, c_ptr
        type(c_ptr), value :: h

@@ -201,6 +201,11 @@ typedef struct {
 int qcoh_oh_create(BoosterHandle booster, const qcoh_oh_config *cfg, qcoh_oh_handle *out);
 int qcoh_oh_run1(qcoh_oh_handle h, const qcoh_run1_in *in, qcoh_run1_out *out);
 int qcoh_oh_free(qcoh_oh_handle h);
+/* Diagnostic exports (OH_GridCompMod.F90:1602-1735, OH_StateSpecs.rc:41-73): copy one derived field of
+ * the last boost step out of HBM.  name (case-sensitive, the DIAG_ suffix of the reference's export):
+ * 3-D [km][ncol]: "TAUCLWDN" "TAUCLIDN" "TAUCLIUP" "TAUCLWUP" "AODUP" "AODDN" "PL" (PL_MOD, Pa) "NDWET"
+ * "OH_boost";  2-D [ncol]: "LAT" "SZA" "stratO3".  out may be host or device memory. */
+int qcoh_oh_get_diag(qcoh_oh_handle h, const char *name, float *out);
 
 /* ---- host mirror of the reference driver -------------------------------------------- */
 /* C mirror of `predict_OH_with_XGB` (OH_GridCompMod.F90:123-398): same arguments in the same

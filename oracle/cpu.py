@@ -194,6 +194,9 @@ def run1(model: Model, fields: dict, consts: dict, *, ohscale=0.85, compute_once
            "NDWET": np.empty((km, ncol), np.float32)}  # fmt: skip
     o.OH, o.OH_boost, o.NDWET = _p(res["OH"]), _p(res["OH_boost"]), _p(res["NDWET"])
     if want_features:
+        res["feat"] = [np.empty(ncol if f in (0, 21, 22, 26) else (km, ncol), np.float32) for f in range(27)]
+        for f in range(27):
+            o.feat3d[f] = _p(res["feat"][f])
         res["X"] = np.empty((km * ncol, 27), np.float32)
         res["pred"] = np.empty(km * ncol, np.float32)
         o.X, o.pred = _p(res["X"]), _p(res["pred"])

@@ -69,7 +69,7 @@ QCOH_SYMBOLS = ("qcoh_version", "qcoh_device_count", "qcoh_set_device", "qcoh_ho
                 "qcoh_booster_parse", "qcoh_booster_get_info", "qcoh_booster_get_flat",
                 "qcoh_dmatrix_create_device", "qcoh_dmatrix_device_ptr", "qcoh_dmatrix_upload", "qcoh_dmatrix_seal",
                 "qcoh_booster_predict_device", "qcoh_set_param", "qcoh_launch_count", "qcoh_oh_create",
-                "qcoh_oh_run1", "qcoh_oh_free", "qcoh_predict_OH_with_XGB", "qcoh_predict_OH_reset",
+                "qcoh_oh_run1", "qcoh_oh_free", "qcoh_oh_get_diag", "qcoh_predict_OH_with_XGB", "qcoh_predict_OH_reset",
                 "qcoh_partition_columns")  # fmt: skip
 
 _LIB = None
@@ -117,6 +117,7 @@ def lib():
         L.qcoh_oh_create.argtypes = [vp, C.POINTER(OhConfig), C.POINTER(vp)]
         L.qcoh_oh_run1.argtypes = [vp, C.POINTER(Run1In), C.POINTER(Run1Out)]
         L.qcoh_oh_free.argtypes = [vp]
+        L.qcoh_oh_get_diag.argtypes = [vp, C.c_char_p, vp]
         L.qcoh_predict_OH_with_XGB.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, vp, vp,
                                                C.POINTER(vp), C.POINTER(C.c_int), vp]  # fmt: skip
         L.qcoh_partition_columns.argtypes = [C.c_int64, C.c_int, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
@@ -406,6 +407,13 @@ class OhRun1:
                 res["pred"] = res["pred"][:n]
         res["diag"] = np.array(list(o.diag))
         return res
+
+    def get_diag(self, name: str) -> np.ndarray:
+        """DIAG_<name> export of the last boost step (OH_StateSpecs.rc:41-73)."""
+        two_d = name in ("LAT", "SZA", "stratO3")
+        out = np.empty(self.ncol if two_d else (self.km, self.ncol), np.float32)
+        check(lib().qcoh_oh_get_diag(self.handle, name.encode(), _ptr(out)))
+        return out
 
     def free(self):
         if self.handle:

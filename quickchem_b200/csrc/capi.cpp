@@ -912,6 +912,30 @@ int qcoh_oh_create(BoosterHandle booster, const qcoh_oh_config *cfg, qcoh_oh_han
   API_END
 }
 
+int qcoh_oh_get_diag(qcoh_oh_handle h, const char *name, float *out) {
+  API_BEGIN
+  Oh *o = O(h);
+  if (!name || !out) throw Error("qcoh_oh_get_diag: NULL argument");
+  if (!o->oh_ml_valid) throw Error("qcoh_oh_get_diag: no boost step has run yet");
+  const size_t n2 = (size_t)o->cfg.ncol, n3 = n2 * o->cfg.km;
+  const std::string s(name);
+  const float *src = nullptr;
+  size_t n = n3;
+  static const char *sum_names[6] = {"TAUCLWDN", "TAUCLIDN", "TAUCLIUP", "TAUCLWUP", "AODUP", "AODDN"};
+  for (int i = 0; i < 6; ++i)
+    if (s == sum_names[i]) src = o->sums[i].p;
+  if (s == "PL") src = o->PL_MOD.p;
+  if (s == "NDWET") src = o->NDWET.p;
+  if (s == "OH_boost") src = o->OH_ML.p;
+  if (s == "LAT") src = o->lat_deg.p, n = n2;
+  if (s == "SZA") src = o->sza.p, n = n2;
+  if (s == "stratO3") src = o->so3.p, n = n2;
+  if (!src) throw Error("qcoh_oh_get_diag: unknown or unavailable field '" + s + "'");
+  deliver(out, src, n);
+  CU(cudaStreamSynchronize(g.stream));
+  API_END
+}
+
 int qcoh_oh_free(qcoh_oh_handle h) {
   API_BEGIN
   Oh *o = O(h);

@@ -204,8 +204,11 @@ __global__ void __launch_bounds__(kBlock, MINB) predict_rows_kernel(DeviceForest
       if (tid == 0) {
         mbar_expect_tx(bar, bytes);
         bulk_g2s((uint32_t)__cvta_generic_to_shared(srow), src, bytes, bar);
+        // one thread polls the mbarrier; 256 threads polling the same word showed up as 1.15 G
+        // shared-memory bank-conflict wavefronts on the LSU data pipe (profiles/README.md, v4)
+        mbar_wait(bar, 0);
       }
-      mbar_wait(bar, 0);
+      __syncthreads();
     } else {
       for (int i = tid; i < n; i += B) srow[i] = __ldg(src + i);
       __syncthreads();

@@ -83,6 +83,24 @@ def test_run1_fused_path_equals_matrix_path(capi, oracle, small_model_path):
         oh.run(oh.make_in(fields), want=("OH", "X"))
 
 
+def test_diag_exports(capi, oracle, small_model_path):
+    """DIAG_* exports (OH_GridCompMod.F90:1602-1735): the derived fields of the last boost step, full
+    [km][ncol] (not only the predicted slab), bit-exact against the oracle's Run1."""
+    fields = synth.raw_fields(6)
+    km, ncol = fields["T"].shape
+    oh = capi.OhRun1(capi.Booster(small_model_path), ncol, km, synth.MAPL)
+    with pytest.raises(capi.QcohError, match="no boost step"):
+        oh.get_diag("AODUP")
+    got = oh.run(oh.make_in(fields), want=("OH", "OH_boost", "NDWET"))
+    ref = oracle.run1(oracle.Model(small_model_path), fields, synth.MAPL, want_features=True)
+    for name, f in (("TAUCLWDN", 15), ("TAUCLIDN", 16), ("TAUCLIUP", 17), ("TAUCLWUP", 18), ("AODUP", 23), ("AODDN", 24),
+                    ("LAT", 0), ("stratO3", 21), ("SZA", 26), ("PL", 1)):  # fmt: skip
+        assert np.array_equal(oh.get_diag(name).view(np.uint32), ref["feat"][f].view(np.uint32)), name
+    assert np.array_equal(oh.get_diag("NDWET"), got["NDWET"]) and np.array_equal(oh.get_diag("OH_boost"), got["OH_boost"])
+    with pytest.raises(capi.QcohError, match="unknown"):
+        oh.get_diag("nope")
+
+
 def test_run1_dynamic_k_range(capi, oracle, small_model_path):
     fields = synth.raw_fields(8)
     got, ref, _, _ = _run_both(capi, oracle, small_model_path, fields, compute_once_per_day=False, nymd=20240229)
