@@ -193,6 +193,10 @@ def main():
 
     dist = None
     if world > 1:
+        # keep stdout to the one JSON line: NCCL's banner / logs go to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         import torch.distributed as dist
 
         torch.cuda.set_device(local)
