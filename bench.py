@@ -137,7 +137,7 @@ def run_reference(args):
     X = np.ascontiguousarray(r["X"])
     n = X.shape[0]
     out = np.empty(n, np.float32)
-    cores = oracle.omp_threads()
+    cores = oracle.use_all_cores()
 
     def step():
         p = model.predict(X)  # orc_dmatrix_from_mat + orc_predict (:347-356)
@@ -325,6 +325,7 @@ def main():
         from oracle import cpu as oracle
 
         oracle.build()
+        oracle.use_all_cores()
         om = oracle.Model(booster_path())
         hs = np.empty((1 << 18, NFEAT), np.float32)
         stride = max(1, ncell // hs.shape[0])

@@ -150,6 +150,13 @@ def omp_threads() -> int:
     return lib().orc_num_threads()
 
 
+def use_all_cores() -> int:
+    """All host cores this process may run on, whatever OMP_NUM_THREADS says (torchrun exports 1)."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    lib().orc_set_num_threads(n)
+    return lib().orc_num_threads()
+
+
 def julian_day(nymd):
     return lib().orc_julian_day(nymd)
 

@@ -64,6 +64,7 @@ typedef struct {
 
 const char *orc_last_error(void);
 int orc_num_threads(void); /* OpenMP threads the predictor uses */
+void orc_set_num_threads(int n); /* override OMP_NUM_THREADS (torchrun sets it to 1) */
 
 /* XGBoosterLoadModel restatement, legacy binary ("binf" optional) only. */
 orc_model *orc_model_load(const char *path);
