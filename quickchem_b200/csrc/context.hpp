@@ -1,0 +1,222 @@
+// context.hpp — shared plumbing of libqcoh's C ABI translation units: error channel, device context,
+// owning buffers, handle types.  Internal; nothing here is exported.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <thread>
+#include <utility>
+#include <vector>
+
+#include "../../include/qcoh.h"
+#include "forest.hpp"
+#include "kernels.hpp"
+
+namespace qcoh {
+
+inline thread_local std::string g_err;
+
+struct Error : std::runtime_error {
+  using std::runtime_error::runtime_error;
+};
+
+#define CU(call)                                                                                      \
+  do {                                                                                                \
+    cudaError_t e__ = (call);                                                                         \
+    if (e__ != cudaSuccess)                                                                           \
+      throw Error(std::string("CUDA error in " #call ": ") + cudaGetErrorName(e__) + " — " +          \
+                  cudaGetErrorString(e__));                                                           \
+  } while (0)
+
+#define API_BEGIN try {
+#define API_END                      \
+  }                                  \
+  catch (const std::exception &e) {  \
+    g_err = e.what();                \
+    return -1;                       \
+  }                                  \
+  catch (...) {                      \
+    g_err = "unknown error";         \
+    return -1;                       \
+  }                                  \
+  return 0;
+
+// ---- device context ---------------------------------------------------------------
+struct Ctx {
+  bool ready = false;
+  int device = -1;
+  cudaStream_t stream = nullptr;       // compute (and everything ordered with it)
+  cudaStream_t copy_stream = nullptr;  // H2D of matrix chunks
+  cudaStream_t d2h_stream = nullptr;   // D2H of result chunks
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  std::vector<cudaEvent_t> chunk_events;
+  int speculate = 1;                   // pipeline prediction into XGDMatrixCreateFromMat
+  uint64_t chunk_rows = 1ull << 21;
+  void *flush = nullptr;
+  size_t flush_bytes = 0;
+  Tunables tun;
+};
+inline Ctx g;
+
+inline int requested_device = -1;
+
+inline void ensure_device() {
+  if (g.ready) return;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) {
+    (void)cudaGetLastError();
+    throw Error(std::string("libqcoh: no CUDA device is visible (") + (e == cudaSuccess ? "device count 0" : cudaGetErrorString(e)) +
+                "); the OH path runs on the GPU only, there is no CPU fallback");
+  }
+  int dev = requested_device;
+  if (dev < 0) {
+    const char *lr = getenv("LOCAL_RANK");
+    dev = lr ? atoi(lr) % n : 0;
+  }
+  if (dev >= n) throw Error("libqcoh: device " + std::to_string(dev) + " requested but only " + std::to_string(n) + " visible");
+  CU(cudaSetDevice(dev));
+  cudaDeviceProp p;
+  CU(cudaGetDeviceProperties(&p, dev));
+  if (p.major < 10)
+    throw Error(std::string("libqcoh is built for sm_100a (B200); device '") + p.name + "' is sm_" + std::to_string(p.major) +
+                std::to_string(p.minor));
+  CU(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
+  CU(cudaStreamCreateWithFlags(&g.copy_stream, cudaStreamNonBlocking));
+  CU(cudaStreamCreateWithFlags(&g.d2h_stream, cudaStreamNonBlocking));
+  CU(cudaEventCreate(&g.ev0));
+  CU(cudaEventCreate(&g.ev1));
+  g.device = dev;
+  g.ready = true;
+}
+
+template <class T>
+struct DevBuf {
+  T *p = nullptr;
+  size_t cap = 0;  // elements
+  T *need(size_t n) {
+    if (n > cap) {
+      if (p) cudaFree(p);
+      p = nullptr, cap = 0;
+      CU(cudaMalloc((void **)&p, (n ? n : 1) * sizeof(T)));
+      cap = n;
+    }
+    return p;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr, cap = 0;
+  }
+  void swap(DevBuf &o) {
+    std::swap(p, o.p);
+    std::swap(cap, o.cap);
+  }
+  DevBuf() = default;
+  DevBuf(const DevBuf &) = delete;
+  DevBuf &operator=(const DevBuf &) = delete;
+  ~DevBuf() { release(); }
+};
+
+template <class T>
+struct PinBuf {
+  T *p = nullptr;
+  size_t cap = 0;
+  T *need(size_t n) {
+    if (n > cap) {
+      if (p) cudaFreeHost(p);
+      p = nullptr, cap = 0;
+      CU(cudaHostAlloc((void **)&p, (n ? n : 1) * sizeof(T), cudaHostAllocDefault));
+      cap = n;
+    }
+    return p;
+  }
+  void swap(PinBuf &o) {
+    std::swap(p, o.p);
+    std::swap(cap, o.cap);
+  }
+  PinBuf() = default;
+  PinBuf(const PinBuf &) = delete;
+  PinBuf &operator=(const PinBuf &) = delete;
+  ~PinBuf() {
+    if (p) cudaFreeHost(p);
+  }
+};
+
+inline bool is_device_ptr(const void *p) {
+  cudaPointerAttributes a;
+  cudaError_t e = cudaPointerGetAttributes(&a, p);
+  if (e != cudaSuccess) {
+    (void)cudaGetLastError();
+    return false;
+  }
+  return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+// ---- handles ------------------------------------------------------------------------
+constexpr uint32_t kBoosterMagic = 0x51434253;  // 'QCBS'
+constexpr uint32_t kDMatrixMagic = 0x5143444d;  // 'QCDM'
+constexpr uint32_t kOhMagic = 0x51434f48;       // 'QCOH'
+
+struct Booster {
+  uint32_t magic = kBoosterMagic;
+  uint64_t version = 0;  // changes with every (re)load
+  bool loaded = false, uploaded = false;
+  HostForest host;
+  FlatForest flat;
+  DeviceForest dev;
+  DevBuf<uint2> d_nodes;
+  DevBuf<uint32_t> d_off;
+  DevBuf<int32_t> d_depth, d_orig;
+  DevBuf<float> d_result;
+  PinBuf<float> h_result;
+};
+
+struct DMatrix {
+  uint32_t magic = kDMatrixMagic;
+  uint64_t nrow = 0, ncol = 0;
+  float missing = NAN;
+  DevBuf<float> X;
+  DevBuf<int> flags;
+  int hflags = 1;  // bit0 has-missing, bit1 has-inf; conservative until sealed
+  bool sealed = false;
+  // prediction pipelined into XGDMatrixCreateFromMat (see create_pipelined)
+  const void *spec_booster = nullptr;
+  uint64_t spec_version = 0;
+  bool spec_ready = false;
+  DevBuf<float> spec_dev;
+  PinBuf<float> spec_host;
+};
+
+// XGDMatrixFree keeps the largest freed matrix buffer for the next XGDMatrixCreateFromMat: the
+// reference creates and frees a same-sized DMatrix on every call (OH_GridCompMod.F90:347,377) and
+// cudaMalloc / cudaFree of multi-GB buffers would otherwise dominate the step.
+inline DevBuf<float> g_spare_X;
+inline PinBuf<float> g_spare_pin;
+inline DevBuf<float> g_spare_spec;
+inline DevBuf<int> g_chunk_flags;
+inline PinBuf<int> g_h_chunk_flags;
+inline Booster *g_last_booster = nullptr;  // the process's booster (the reference keeps exactly one, SAVE :182)
+inline uint64_t g_version_counter = 0;
+
+inline Booster *B(BoosterHandle h) {
+  Booster *b = (Booster *)h;
+  if (!b || b->magic != kBoosterMagic) throw Error("Invalid booster handle");
+  return b;
+}
+inline DMatrix *D(DMatrixHandle h) {
+  DMatrix *d = (DMatrix *)h;
+  if (!d || d->magic != kDMatrixMagic) throw Error("Invalid DMatrix handle");
+  return d;
+}
+
+// capi_xgb.cpp
+void upload(Booster *b);
+
+}  // namespace qcoh
