@@ -1,4 +1,4 @@
-// kernels.hpp — launch interface of the sm_100a kernels (kernels.cu), used by capi.cpp.
+// kernels.hpp — launch interface of the sm_100a kernels (kernels.cu), used by capi_xgb.cpp / capi_oh.cpp.
 #pragma once
 #include <cuda_runtime.h>
 
