@@ -231,6 +231,7 @@ int qcoh_oh_run1(qcoh_oh_handle h, const qcoh_run1_in *in, qcoh_run1_out *out) {
     for (int i = 0; i < 6; ++i) r.sums[i] = o->sums[i].need(n3);
     r.lat_deg = o->lat_deg.need(n2), r.so3 = o->so3.need(n2);
     CU(launch_oh_sums(r, g.stream));
+    sync_const_top(o->booster);
     CU(cudaMemsetAsync(r.OH_ML, 0, n3 * 4, g.stream));  // self%OH_ML = 0.0 (:1559)
     if (npred && !out->X) {
       // fused: pack (:303-345) + create (:347) + predict (:356) + 10**x (:369) * OHscale (:1569) in one

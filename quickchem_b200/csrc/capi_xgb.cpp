@@ -28,6 +28,7 @@ void upload(Booster *b) {
       dev_nodes[2 * i] = 0u - key;  // key >= 0x007FFFFF (-inf), never 0
     }
     CU(cudaMemcpy(b->d_nodes.need(nn), dev_nodes.data(), nn * 8, cudaMemcpyHostToDevice));
+    b->dev_nodes_host = std::move(dev_nodes);
   }
   CU(cudaMemcpy(b->d_off.need(f.tree_offset.size()), f.tree_offset.data(), f.tree_offset.size() * 4, cudaMemcpyHostToDevice));
   CU(cudaMemcpy(b->d_depth.need(f.tree_depth.size()), f.tree_depth.data(), f.tree_depth.size() * 4, cudaMemcpyHostToDevice));
@@ -55,6 +56,23 @@ void upload(Booster *b) {
   b->uploaded = true;
 }
 
+// the constant-memory table of tree tops belongs to one booster at a time
+static uint64_t g_const_top_owner = 0;
+static int g_const_top_levels = 0;
+void sync_const_top(Booster *b) {
+  const int want = g.tun.top_levels < 0 ? 4 : g.tun.top_levels;
+  b->dev.const_top_levels = 0;
+  if (want <= 0) return;
+  if (g_const_top_owner != b->version || g_const_top_levels != want) {
+    if (upload_const_top(b->dev_nodes_host.data(), b->flat.tree_offset.data(), b->dev.ntree, want, g.stream) != cudaSuccess) {
+      (void)cudaGetLastError();
+      return;  // does not fit: the kernel runs without the table
+    }
+    g_const_top_owner = b->version, g_const_top_levels = want;
+  }
+  b->dev.const_top_levels = want;
+}
+
 static void seal(DMatrix *d) {
   ensure_device();
   int *fl = d->flags.need(1);
@@ -79,6 +97,7 @@ static void predict_into(Booster *b, DMatrix *d, int option_mask, unsigned ntree
   if (d->ncol > b->host.num_feature)
     throw Error("Check failed: Number of columns does not match number of features in booster. Columns: " +
                 std::to_string(d->ncol) + " Features: " + std::to_string(b->host.num_feature));
+  sync_const_top(b);
   PredictArgs a;
   a.X = d->X.p, a.nrow = d->nrow, a.ncol = (int32_t)d->ncol, a.missing = d->missing;
   a.has_missing = ((d->hflags & 1) || d->ncol < b->host.num_feature) ? 1 : 0;
@@ -161,6 +180,7 @@ static void create_pipelined(DMatrix *d, const float *data, Booster *b) {
   float *sdev = nullptr, *shost = nullptr;
   if (spec) {
     upload(b);
+    sync_const_top(b);
     if (g_spare_spec.cap >= nrow && g_spare_spec.p) d->spec_dev.swap(g_spare_spec);
     sdev = d->spec_dev.need(nrow);
     if (g_spare_pin.cap >= nrow && g_spare_pin.p) d->spec_host.swap(g_spare_pin);

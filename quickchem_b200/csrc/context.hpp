@@ -170,6 +170,7 @@ struct Booster {
   bool loaded = false, uploaded = false;
   HostForest host;
   FlatForest flat;
+  std::vector<uint32_t> dev_nodes_host;  // the device form of the nodes (keys), kept for the constant-top table
   DeviceForest dev;
   DevBuf<uint2> d_nodes;
   DevBuf<uint32_t> d_off;
@@ -218,5 +219,6 @@ inline DMatrix *D(DMatrixHandle h) {
 
 // capi_xgb.cpp
 void upload(Booster *b);
+void sync_const_top(Booster *b);  // make the constant-memory table of tree tops hold this booster
 
 }  // namespace qcoh

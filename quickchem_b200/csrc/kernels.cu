@@ -94,9 +94,30 @@ __device__ __forceinline__ uint32_t step_index(uint32_t idx, uint32_t rel, uint3
   return idx;
 }
 
+// Top of every tree in constant memory (experiment, Tunables::top_levels): the first 2^CTOP - 1 nodes of
+// a tree in breadth-first order are exactly its levels 0..CTOP-1.  Constant loads go through the
+// constant cache, not the LSU / TEX data pipes; lanes of a warp mostly agree at those levels, so the
+// per-address serialisation of divergent constant loads stays short.
+constexpr int kConstTopNodes = 8000;  // 64 000 B of the 64 KB constant bank
+__constant__ uint2 c_top[kConstTopNodes];
+
+cudaError_t upload_const_top(const uint32_t *dev_nodes_xy, const uint32_t *tree_offset, int ntree, int levels, cudaStream_t s) {
+  const int stride = 1 << levels;
+  if (levels <= 0 || (int64_t)ntree * stride > kConstTopNodes) return cudaErrorInvalidValue;
+  static uint2 host[kConstTopNodes];
+  for (int t = 0; t < ntree; ++t) {
+    const uint32_t n0 = tree_offset[t], n1 = tree_offset[t + 1];
+    for (int i = 0; i < stride; ++i) {
+      const uint32_t n = n0 + (uint32_t)i;
+      host[t * stride + i] = n < n1 ? make_uint2(dev_nodes_xy[2 * n], dev_nodes_xy[2 * n + 1]) : make_uint2(0u, 0u);
+    }
+  }
+  return cudaMemcpyToSymbolAsync(c_top, host, sizeof(uint2) * (size_t)ntree * stride, 0, cudaMemcpyHostToDevice, s);
+}
+
 // TEXMODE is a bit mask over the ILP trees in flight: tree j fetches its nodes through the texture pipe
 // (tex1Dfetch on the same buffer) if bit j is set, through the LSU (LDG) otherwise.
-template <int ILP, bool HAS_MISSING, bool PARK, int TEXMODE = 0>
+template <int ILP, bool HAS_MISSING, bool PARK, int TEXMODE = 0, int CTOP = 0>
 __device__ __forceinline__ void walk_group(const uint2 *__restrict__ nodes, cudaTextureObject_t tex, const uint32_t *__restrict__ toff,
                                            const int32_t *__restrict__ tdepth, int t, uint32_t my_saddr,
                                            uint32_t (&idx)[ILP], uint32_t (&xbits)[ILP]) {
@@ -115,7 +136,38 @@ __device__ __forceinline__ void walk_group(const uint2 *__restrict__ nodes, cuda
   // own leaf line at every remaining level, and at the deep levels those are up to 32 different
   // lines per warp request; the L1TEX data pipe is the bound of this kernel.  The
   // fetch is predicated, so nd[j] keeps the leaf node and no per-level copy of the value is needed.
-  for (int d = 0; d <= depth; ++d) {
+  auto visit = [&](int j) {
+    // shared address of srow[feat][tid] = my_saddr + feat * (kBlock * 4): the top byte of the meta word
+    // is feat * 4, so moving it to byte 1 (one PRMT) gives feat * 1024
+    static_assert(kBlock * 4 == 1024 && kMetaFeatShift == 26, "address trick assumes a 1 KB feature stride");
+    const uint32_t sa = my_saddr + __byte_perm(nd[j].y, 0u, 0x4434);
+    uint32_t kv;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(kv) : "r"(sa));
+    rel[j] = nd[j].y & kMetaRelMask;
+    if (HAS_MISSING && kv == kKeyMissing)  // default child: left = idx + rel, right = left + 1
+      idx[j] += rel[j] + ((nd[j].y & kMetaDefaultLeftBit) ? 0u : (rel[j] != 0u ? 1u : 0u));
+    else
+      idx[j] = step_index(idx[j], rel[j], nd[j].x, kv);
+  };
+  if (CTOP > 0) {
+    uint32_t cbase[ILP];  // index of this tree's table row minus its first node
+#pragma unroll
+    for (int j = 0; j < ILP; ++j) cbase[j] = ((uint32_t)(t + j) << CTOP) - idx[j];
+#pragma unroll
+    for (int d = 0; d < CTOP; ++d) {
+      if (d <= depth) {
+#pragma unroll
+        for (int j = 0; j < ILP; ++j) {
+          if (!PARK || rel[j] != 0u) {
+            nd[j] = c_top[cbase[j] + idx[j]];
+            visit(j);
+          }
+          if (PARK) asm volatile("" : "+r"(rel[j]));
+        }
+      }
+    }
+  }
+  for (int d = CTOP; d <= depth; ++d) {
 #pragma unroll
     for (int j = 0; j < ILP; ++j) {
       if (!PARK || rel[j] != 0u) {
@@ -123,17 +175,7 @@ __device__ __forceinline__ void walk_group(const uint2 *__restrict__ nodes, cuda
           nd[j] = tex1Dfetch<uint2>(tex, (int)idx[j]);
         else
           nd[j] = __ldg(nodes + idx[j]);
-        // shared address of srow[feat][tid] = my_saddr + feat * (kBlock * 4): the top byte of the meta word
-        // is feat * 4, so moving it to byte 1 (one PRMT) gives feat * 1024
-        static_assert(kBlock * 4 == 1024 && kMetaFeatShift == 26, "address trick assumes a 1 KB feature stride");
-        const uint32_t sa = my_saddr + __byte_perm(nd[j].y, 0u, 0x4434);
-        uint32_t kv;
-        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(kv) : "r"(sa));
-        rel[j] = nd[j].y & kMetaRelMask;
-        if (HAS_MISSING && kv == kKeyMissing)  // default child: left = idx + rel, right = left + 1
-          idx[j] += rel[j] + ((nd[j].y & kMetaDefaultLeftBit) ? 0u : (rel[j] != 0u ? 1u : 0u));
-        else
-          idx[j] = step_index(idx[j], rel[j], nd[j].x, kv);
+        visit(j);
       }
       // keep "still walking" in the rel register only (one ISETP per level instead of predicate shuffling)
       if (PARK) asm volatile("" : "+r"(rel[j]));
@@ -178,7 +220,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       : "memory");
 }
 
-template <int ILP, bool HAS_MISSING, bool PRED_LEAF, bool PARK, int MINB, int TEXMODE = 0>
+template <int ILP, bool HAS_MISSING, bool PRED_LEAF, bool PARK, int MINB, int TEXMODE = 0, int CTOP = 0>
 __global__ void __launch_bounds__(kBlock, MINB) predict_rows_kernel(DeviceForest f, PredictArgs a) {
   extern __shared__ __align__(128) float srow[];
   uint32_t *skey = reinterpret_cast<uint32_t *>(srow);  // the transposed tile holds keys, not floats
@@ -241,7 +283,7 @@ __global__ void __launch_bounds__(kBlock, MINB) predict_rows_kernel(DeviceForest
   int t = 0;
   for (; t + ILP <= ntree; t += ILP) {
     uint32_t idx[ILP], xb[ILP];
-    walk_group<ILP, HAS_MISSING, PARK, TEXMODE>(f.nodes, f.tex, f.tree_offset, f.tree_depth, t, my, idx, xb);
+    walk_group<ILP, HAS_MISSING, PARK, TEXMODE, CTOP>(f.nodes, f.tex, f.tree_offset, f.tree_depth, t, my, idx, xb);
 #pragma unroll
     for (int j = 0; j < ILP; ++j) {
       if (PRED_LEAF) {
@@ -269,13 +311,13 @@ __global__ void __launch_bounds__(kBlock, MINB) predict_rows_kernel(DeviceForest
 // field, so every load is coalesced and lands directly in the transposed tile — the [N x 27] matrix is
 // never formed, and no transposition is needed.  Whether a tile holds missing entries is decided per
 // tile (block-wide OR) and selects the walk specialisation at run time; +-inf raises the error flag.
-template <int ILP, bool HAS_MISSING, bool PARK, int TEXMODE>
+template <int ILP, bool HAS_MISSING, bool PARK, int TEXMODE, int CTOP>
 __device__ __forceinline__ float forest_sum(const DeviceForest &f, uint32_t my, int ntree) {
   float acc = f.base_score;
   int t = 0;
   for (; t + ILP <= ntree; t += ILP) {
     uint32_t idx[ILP], xb[ILP];
-    walk_group<ILP, HAS_MISSING, PARK, TEXMODE>(f.nodes, f.tex, f.tree_offset, f.tree_depth, t, my, idx, xb);
+    walk_group<ILP, HAS_MISSING, PARK, TEXMODE, CTOP>(f.nodes, f.tex, f.tree_offset, f.tree_depth, t, my, idx, xb);
 #pragma unroll
     for (int j = 0; j < ILP; ++j) acc = __fadd_rn(acc, __uint_as_float(xb[j]));
   }
@@ -287,7 +329,7 @@ __device__ __forceinline__ float forest_sum(const DeviceForest &f, uint32_t my, 
   return acc;
 }
 
-template <int TEXMODE>
+template <int TEXMODE, int CTOP>
 __global__ void __launch_bounds__(kBlock, 6) predict_soa_kernel(DeviceForest f, SoaArgs a) {
   extern __shared__ __align__(128) float srow[];
   uint32_t *skey = reinterpret_cast<uint32_t *>(srow);
@@ -326,9 +368,9 @@ __global__ void __launch_bounds__(kBlock, 6) predict_soa_kernel(DeviceForest f, 
   const uint32_t my = (uint32_t)__cvta_generic_to_shared(srow + tid);
   float acc;
   if (tile_missing)
-    acc = forest_sum<4, true, true, TEXMODE>(f, my, a.ntree_used);
+    acc = forest_sum<4, true, true, TEXMODE, CTOP>(f, my, a.ntree_used);
   else
-    acc = forest_sum<4, false, true, TEXMODE>(f, my, a.ntree_used);
+    acc = forest_sum<4, false, true, TEXMODE, CTOP>(f, my, a.ntree_used);
   if (a.pred) a.pred[m] = acc;
   a.out[m] = export_transform(acc, a.exp10, a.scale);
 }
@@ -340,21 +382,21 @@ cudaError_t launch_predict_soa(const DeviceForest &f, const SoaArgs &a, const Tu
   const uint64_t nblk = (a.nrow + kBlock - 1) / kBlock;
   if (nblk > 0x7fffffffull) return cudaErrorInvalidConfiguration;
   const bool tex = f.tex != 0 && t.variant >= 0;
-  auto k = tex ? predict_soa_kernel<0xA> : predict_soa_kernel<0>;
+  auto k = !tex ? predict_soa_kernel<0, 0> : (f.const_top_levels == 4 ? predict_soa_kernel<0xA, 4> : predict_soa_kernel<0xA, 0>);
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   k<<<dim3((unsigned)nblk), kBlock, smem, s>>>(f, a);
   return QC_LAUNCHED();
 }
 
-template <int ILP, bool HM, bool PL, bool PARK, int MINB, int TEXMODE = 0>
+template <int ILP, bool HM, bool PL, bool PARK, int MINB, int TEXMODE = 0, int CTOP = 0>
 static cudaError_t launch_predict_one(const DeviceForest &f, const PredictArgs &a, cudaStream_t s) {
   // srow holds max(ncol, nfeat + 1) feature slots per thread
   const int slots = (f.nfeat + 1) > a.ncol ? (f.nfeat + 1) : a.ncol;
   const size_t smem = (size_t)kBlock * slots * sizeof(float);
   const uint64_t nblk = (a.nrow + kBlock - 1) / kBlock;
   if (nblk > 0x7fffffffull) return cudaErrorInvalidConfiguration;
-  auto k = predict_rows_kernel<ILP, HM, PL, PARK, MINB, TEXMODE>;
+  auto k = predict_rows_kernel<ILP, HM, PL, PARK, MINB, TEXMODE, CTOP>;
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   k<<<dim3((unsigned)nblk), kBlock, smem, s>>>(f, a);
@@ -364,30 +406,34 @@ static cudaError_t launch_predict_one(const DeviceForest &f, const PredictArgs &
 cudaError_t launch_predict(const DeviceForest &f, const PredictArgs &a, const Tunables &t, cudaStream_t s) {
   if (a.nrow == 0) return cudaSuccess;
   if (a.ncol > 32 || f.nfeat > 31) return cudaErrorInvalidValue;  // staged through 32 registers (forest.hpp kMaxFeatures)
-  // Default build: 4 trees in flight per thread, trees 1 and 3 of each group fetch their nodes through
-  // the texture pipe, trees 0 and 2 through the LSU (mask 0xA).  The kernel is bound by the L1TEX
-  // data pipe; the two front ends have separate writeback paths, and splitting the gathers between
-  // them measured +10 % (profiles/README.md).  All-TEX is slower than all-LSU.
+  // Default build: 4 trees in flight per thread; levels 0..3 of every tree come from constant memory;
+  // below that, trees 1 and 3 of each group fetch their nodes through the texture pipe and trees 0 and
+  // 2 through the LSU (mask 0xA).  The kernel is bound by the L1TEX data pipes: the two front ends have
+  // separate wavefront / writeback budgets (+10 %), and the constant cache takes the coherent top
+  // levels off both (+8 %; 5 levels and more lose to the serialisation of divergent constant loads).
+  // All-TEX is slower than all-LSU.  Measurements: profiles/README.md.
   constexpr int kTex = 0xA;
   const bool tex = f.tex != 0 && t.variant >= 0;
+  const int ctop = f.const_top_levels;  // 0 if the table does not hold this booster
   if (a.pred_leaf) {
     if (a.has_missing)
       return tex ? launch_predict_one<4, true, true, true, 6, kTex>(f, a, s) : launch_predict_one<4, true, true, true, 6, 0>(f, a, s);
     return tex ? launch_predict_one<4, false, true, true, 6, kTex>(f, a, s) : launch_predict_one<4, false, true, true, 6, 0>(f, a, s);
   }
-  if (a.has_missing)
+  if (a.has_missing) {
+    if (tex && ctop == 4) return launch_predict_one<4, true, false, true, 6, kTex, 4>(f, a, s);
     return tex ? launch_predict_one<4, true, false, true, 6, kTex>(f, a, s) : launch_predict_one<4, true, false, true, 6, 0>(f, a, s);
-  // clean matrix, sums: the production path.  Experiments (qcoh_set_param): park, ilp, minb, variant.
+  }
+  // clean matrix, sums: the production path.  Experiments (qcoh_set_param): park, ilp, minb, variant, top_levels.
   if (t.park == 0) return launch_predict_one<4, false, false, false, 6, 0>(f, a, s);
   if (t.variant > 0 && f.tex) {
-#define QC_TEX(V, I, MASK) \
-  if (t.variant == V) return launch_predict_one<I, false, false, true, 6, MASK>(f, a, s);
+#define QC_TEX(V, I, MASK)                                                                  \
+  if (t.variant == V)                                                                        \
+    return ctop == 4 ? launch_predict_one<I, false, false, true, 6, MASK, 4>(f, a, s)        \
+                     : launch_predict_one<I, false, false, true, 6, MASK, 0>(f, a, s);
     QC_TEX(1, 4, 0xF) QC_TEX(2, 4, 0xA) QC_TEX(3, 4, 0x8) QC_TEX(4, 4, 0xE)
     QC_TEX(5, 3, 0x4) QC_TEX(6, 3, 0x6) QC_TEX(7, 6, 0x2A) QC_TEX(8, 6, 0x24) QC_TEX(9, 8, 0xAA)
     QC_TEX(10, 2, 0x2) QC_TEX(11, 5, 0x0A) QC_TEX(12, 5, 0x15)
-    QC_TEX(13, 6, 0x36) QC_TEX(14, 5, 0x1E) QC_TEX(15, 8, 0xEE) QC_TEX(16, 6, 0x3E) QC_TEX(17, 7, 0x5A) QC_TEX(18, 7, 0x6D)
-    if (t.variant == 20) return launch_predict_one<4, false, false, true, 5, 0xA>(f, a, s);
-    if (t.variant == 21) return launch_predict_one<4, false, false, true, 4, 0xA>(f, a, s);
 #undef QC_TEX
   }
   if (t.ilp > 0 || t.minb > 0 || !tex) {  // LSU-only builds
@@ -401,7 +447,13 @@ cudaError_t launch_predict(const DeviceForest &f, const PredictArgs &a, const Tu
 #undef QC_CASE
     return launch_predict_one<3, false, false, true, 6, 0>(f, a, s);
   }
-  return launch_predict_one<4, false, false, true, 6, kTex>(f, a, s);
+  switch (ctop) {
+    case 3: return launch_predict_one<4, false, false, true, 6, kTex, 3>(f, a, s);
+    case 4: return launch_predict_one<4, false, false, true, 6, kTex, 4>(f, a, s);
+    case 5: return launch_predict_one<4, false, false, true, 6, kTex, 5>(f, a, s);
+    case 6: return launch_predict_one<4, false, false, true, 6, kTex, 6>(f, a, s);
+    default: return launch_predict_one<4, false, false, true, 6, kTex, 0>(f, a, s);
+  }
 }
 
 // =====================================================================================

@@ -13,6 +13,7 @@ struct DeviceForest {
   const int32_t *tree_depth = nullptr;   // [ntree]
   const int32_t *orig_id = nullptr;      // [num_nodes]
   cudaTextureObject_t tex = 0;           // the same nodes as a 1-D linear uint2 texture (TEX pipe)
+  int const_top_levels = 0;              // levels of every tree currently held in the constant-memory table
   int32_t ntree = 0;
   int32_t nfeat = 0;
   int32_t max_depth = 0;
@@ -37,12 +38,15 @@ struct Tunables {
   int variant = 0;   // 0 = default
   int ilp = 0;       // trees walked concurrently per thread (0 = default)
   int block = 0;     // threads per CTA (0 = default)
-  int top_levels = 0;
+  int top_levels = -1;  // tree levels served from constant memory: -1 = default (4), 0 = none
   int park = -1;     // -1 = default (on)
   int minb = 0;      // min resident CTAs per SM the kernel is compiled for (register budget)
 };
 
 uint64_t launch_count();
+
+// (experiment) copy levels 0..levels-1 of every tree into the kernel's __constant__ table
+cudaError_t upload_const_top(const uint32_t *dev_nodes_xy, const uint32_t *tree_offset, int ntree, int levels, cudaStream_t s);
 
 // flags[0] |= 1 if any entry is NaN or == missing; flags[0] |= 2 if any entry is +-inf
 // (and `missing` is finite) — what XGDMatrixCreateFromMat checks (xgboost src/data/data.cc).

@@ -213,14 +213,23 @@ def test_kernel_variants_agree(capi, oracle, small_model_path, small_forest):
         capi.set_param("ilp", 0)
         capi.set_param("minb", 0)
         capi.set_param("park", -1)
-        for variant in (-1, 0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12):  # LSU / texture-pipe mixes
-            capi.set_param("variant", variant)
-            assert np.array_equal(b.predict(d).view(np.uint32), ref.view(np.uint32)), variant
+        for top in (0, 3, 4, 5, 6, -1):  # tree levels served from constant memory
+            capi.set_param("top_levels", top)
+            for variant in (-1, 0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12):  # LSU / texture-pipe mixes
+                capi.set_param("variant", variant)
+                assert np.array_equal(b.predict(d).view(np.uint32), ref.view(np.uint32)), (top, variant)
+        capi.set_param("variant", 0)
+        xm = inject_specials(x, small_forest, np.random.default_rng(5))  # the has-missing build with the table
+        refm = oracle.Model(small_model_path).predict(xm)
+        for top in (0, 4):
+            capi.set_param("top_levels", top)
+            assert np.array_equal(b.predict(capi.DMatrix(xm)).view(np.uint32), refm.view(np.uint32)), top
     finally:
         capi.set_param("ilp", 0)
         capi.set_param("minb", 0)
         capi.set_param("park", -1)
         capi.set_param("variant", 0)
+        capi.set_param("top_levels", -1)
 
 
 def test_pipelined_create_matches_plain_path(capi, oracle, tmp_path, small_model_path, small_forest):

@@ -83,12 +83,16 @@ for (t, d), p in paths.items():
 b = capi.Booster(paths[max(paths)])
 oh = capi.OhRun1(b, ncol, km, synth.MAPL)  # 40 hPa slab as in production
 ro = capi.Run1Out(); ro.OH = oh_out.ptr
-t_steps = []
-for hour in range(24):
-    rin = oh.make_in(dev, nymd=20220701, need_to_call_boost=(hour == 0))
-    capi.synchronize(); t0 = time.perf_counter()
-    capi.check(capi.lib().qcoh_oh_run1(oh.handle, capi.C.byref(rin), capi.C.byref(ro)))
-    t_steps.append((time.perf_counter() - t0) * 1e3)
-print(json.dumps(dict(day="24 hourly steps, compute_once_per_day, device-resident fields", grid=a.grid, k1=ro.k1,
+k1 = 0
+for day in range(2):  # day 0 warms up (allocations, lazy kernel load, SZA cache); day 1 is timed
+    t_steps = []
+    for hour in range(24):
+        rin = oh.make_in(dev, nymd=20220701 + day, need_to_call_boost=(hour == 0))
+        capi.synchronize(); t0 = time.perf_counter()
+        capi.check(capi.lib().qcoh_oh_run1(oh.handle, capi.C.byref(rin), capi.C.byref(ro)))
+        t_steps.append((time.perf_counter() - t0) * 1e3)
+        if hour == 0:
+            k1 = ro.k1
+print(json.dumps(dict(day="24 hourly steps, compute_once_per_day, device-resident fields (2nd day timed)", grid=a.grid, k1=k1,
                       boost_step_ms=round(t_steps[0], 2), other_step_ms=round(float(np.median(t_steps[1:])), 3),
                       day_ms=round(sum(t_steps), 2))), flush=True)
