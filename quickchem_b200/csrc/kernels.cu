@@ -65,10 +65,10 @@ cudaError_t launch_fill(float *p, uint64_t n, float v, cudaStream_t s) {
 // =====================================================================================
 // One thread = one row (grid cell).  The CTA's rows are staged in shared memory TRANSPOSED,
 // srow[f][tid]: whatever feature each lane asks for, lane L always hits bank L — the
-// data-dependent feature fetch is bank-conflict-free by construction.  Slot `nfeat` of every row
-// holds -inf: leaves are encoded with feat = nfeat and rel = 0, so `!(v < x)` is false there and
-// the walk self-loops — the descent is a fixed-trip-count loop with no leaf test and no
-// divergent branch.  Missing entries (NaN or == missing) are canonicalised to NaN while staging.
+// data-dependent feature fetch is bank-conflict-free by construction.  The tile holds order-preserving
+// integer keys of the values (below); slot `nfeat` of every row holds key 0: leaves are encoded with
+// feat = nfeat and rel = 0, so the compare never says "right" there and the walk self-loops — no leaf
+// test inside the descent.  Missing entries (NaN or == missing) become key 0xFFFFFFFF while staging.
 //
 // XGBoost semantics restated (xgboost 1.6.0 src/predictor/predict_fn.h GetNextNode,
 // src/predictor/cpu_predictor.cc PredictByAllTrees): missing -> default child, else
@@ -94,7 +94,7 @@ __device__ __forceinline__ uint32_t step_index(uint32_t idx, uint32_t rel, uint3
   return idx;
 }
 
-// Top of every tree in constant memory (experiment, Tunables::top_levels): the first 2^CTOP - 1 nodes of
+// Top of every tree in constant memory (Tunables::top_levels, default 4): the first 2^CTOP - 1 nodes of
 // a tree in breadth-first order are exactly its levels 0..CTOP-1.  Constant loads go through the
 // constant cache, not the LSU / TEX data pipes; lanes of a warp mostly agree at those levels, so the
 // per-address serialisation of divergent constant loads stays short.
