@@ -31,7 +31,16 @@ void upload(Booster *b) {
     b->dev_nodes_host = std::move(dev_nodes);
   }
   CU(cudaMemcpy(b->d_off.need(f.tree_offset.size()), f.tree_offset.data(), f.tree_offset.size() * 4, cudaMemcpyHostToDevice));
-  CU(cudaMemcpy(b->d_depth.need(f.tree_depth.size()), f.tree_depth.data(), f.tree_depth.size() * 4, cudaMemcpyHostToDevice));
+  {
+    // device form: max leaf depth | min leaf depth << 8 (a tree whose shallowest leaf is below the levels
+    // held in constant memory needs no leaf handling there)
+    std::vector<int32_t> dd(f.tree_depth.size());
+    for (size_t i = 0; i < dd.size(); ++i) {
+      if (f.tree_depth[i] > 255) throw Error("tree " + std::to_string(i) + " is deeper than 255 levels");
+      dd[i] = f.tree_depth[i] | (std::min(f.tree_min_leaf_depth[i], 255) << 8);
+    }
+    CU(cudaMemcpy(b->d_depth.need(dd.size()), dd.data(), dd.size() * 4, cudaMemcpyHostToDevice));
+  }
   CU(cudaMemcpy(b->d_orig.need(nn), f.orig_id.data(), nn * 4, cudaMemcpyHostToDevice));
   b->dev.nodes = b->d_nodes.p, b->dev.tree_offset = b->d_off.p, b->dev.tree_depth = b->d_depth.p, b->dev.orig_id = b->d_orig.p;
   b->dev.ntree = (int32_t)b->host.trees.size();

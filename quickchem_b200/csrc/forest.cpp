@@ -751,7 +751,7 @@ FlatForest flatten(const HostForest &f) {
       order.push_back(r), depth.push_back(depth[h] + 1);
     }
     if (order.size() > kMetaRelMask) fail("tree " + std::to_string(ti) + " has too many nodes for the 23-bit child offset");
-    int32_t maxd = 0;
+    int32_t maxd = 0, mind = 1 << 30;
     for (size_t h = 0; h < order.size(); ++h) {
       const int32_t o = order[h];
       uint32_t xbits, meta;
@@ -759,6 +759,7 @@ FlatForest flatten(const HostForest &f) {
       if (t.cleft[o] == -1) {
         meta = (f.num_feature << kMetaFeatShift) | kMetaDefaultLeftBit;  // rel = 0: self-loop
         if (depth[h] > maxd) maxd = depth[h];
+        if (depth[h] < mind) mind = depth[h];
         if (!std::isfinite(t.info[(size_t)o]))
           fail("tree " + std::to_string(ti) + " node " + std::to_string(o) + ": non-finite leaf value");
       } else {
@@ -771,6 +772,7 @@ FlatForest flatten(const HostForest &f) {
     }
     (void)base;
     out.tree_depth.push_back(maxd);
+    out.tree_min_leaf_depth.push_back(mind);
     if (maxd > out.max_depth) out.max_depth = maxd;
     out.tree_offset.push_back((uint32_t)out.orig_id.size());
   }

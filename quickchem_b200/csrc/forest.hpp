@@ -51,6 +51,7 @@ struct FlatForest {
   std::vector<uint32_t> nodes_xy;     // 2 words per node
   std::vector<uint32_t> tree_offset;  // [ntree + 1], in nodes
   std::vector<int32_t> tree_depth;    // [ntree] depth of the deepest leaf (root = 0)
+  std::vector<int32_t> tree_min_leaf_depth;  // [ntree] depth of the shallowest leaf
   std::vector<int32_t> orig_id;       // flattened position -> XGBoost node id (pred_leaf output)
   int32_t max_depth = 0;
   int64_t num_nodes() const { return (int64_t)orig_id.size(); }

@@ -121,13 +121,15 @@ template <int ILP, bool HAS_MISSING, bool PARK, int TEXMODE = 0, int CTOP = 0>
 __device__ __forceinline__ void walk_group(const uint2 *__restrict__ nodes, cudaTextureObject_t tex, const uint32_t *__restrict__ toff,
                                            const int32_t *__restrict__ tdepth, int t, uint32_t my_saddr,
                                            uint32_t (&idx)[ILP], uint32_t (&xbits)[ILP]) {
-  int depth = 0;
+  int depth = 0, minleaf = 255;  // tdepth[] = deepest leaf | shallowest leaf << 8
   uint2 nd[ILP];
   uint32_t rel[ILP];
 #pragma unroll
   for (int j = 0; j < ILP; ++j) {
     idx[j] = __ldg(toff + t + j);
-    depth = max(depth, __ldg(tdepth + t + j));
+    const int dd = __ldg(tdepth + t + j);
+    depth = max(depth, dd & 0xFF);
+    minleaf = min(minleaf, dd >> 8);
     nd[j] = make_uint2(0u, 0u);
     rel[j] = 1u;
   }
@@ -153,16 +155,29 @@ __device__ __forceinline__ void walk_group(const uint2 *__restrict__ nodes, cuda
     uint32_t cbase[ILP];  // index of this tree's table row minus its first node
 #pragma unroll
     for (int j = 0; j < ILP; ++j) cbase[j] = ((uint32_t)(t + j) << CTOP) - idx[j];
+    if (minleaf >= CTOP) {
+      // no leaf above level CTOP in any of these trees (the usual case for deep trees): every lane walks
+      // all CTOP levels — no park predicate, no branches
 #pragma unroll
-    for (int d = 0; d < CTOP; ++d) {
-      if (d <= depth) {
+      for (int d = 0; d < CTOP; ++d) {
 #pragma unroll
         for (int j = 0; j < ILP; ++j) {
-          if (!PARK || rel[j] != 0u) {
-            nd[j] = c_top[cbase[j] + idx[j]];
-            visit(j);
+          nd[j] = c_top[cbase[j] + idx[j]];
+          visit(j);
+        }
+      }
+    } else {
+#pragma unroll
+      for (int d = 0; d < CTOP; ++d) {
+        if (d <= depth) {
+#pragma unroll
+          for (int j = 0; j < ILP; ++j) {
+            if (!PARK || rel[j] != 0u) {
+              nd[j] = c_top[cbase[j] + idx[j]];
+              visit(j);
+            }
+            if (PARK) asm volatile("" : "+r"(rel[j]));
           }
-          if (PARK) asm volatile("" : "+r"(rel[j]));
         }
       }
     }
