@@ -51,7 +51,8 @@ int XGDMatrixSaveBinary(DMatrixHandle handle, const char *fname, int silent);
 /* xgb_fortran_api.F90:44-49 (wrapper :156-161); call sites OH_GridCompMod.F90:264,377. */
 int XGDMatrixFree(DMatrixHandle handle);
 
-/* xgb_fortran_api.F90:52-59 (wrapper :165-174).  Unused by OH.  Reads a "QCDM" file. */
+/* xgb_fortran_api.F90:52-59 (wrapper :165-174).  Unused by OH.  Reads a "QCDM" file, libsvm text, or
+ * csv ("<path>?format=csv[&label_column=N]") like libxgboost's URI; XGBoost's binary DMatrix is not read. */
 int XGDMatrixCreateFromFile(const char *fname, int silent, DMatrixHandle *out);
 
 /* xgb_fortran_api.F90:61-73; call site OH_GridCompMod.F90:356 (option_mask=0, ntree_limit=0,

@@ -413,24 +413,110 @@ int XGDMatrixSaveBinary(DMatrixHandle handle, const char *fname, int silent) {
   API_END
 }
 
+// Text inputs libxgboost's XGDMatrixCreateFromFile also takes: libsvm ("label idx:val idx:val ...", the
+// default) and csv ("<path>?format=csv[&label_column=N]").  Entries a libsvm row does not list are missing;
+// the label column is parsed and dropped (prediction does not use it).
+static void parse_text_matrix(const std::string &uri, std::vector<float> &h, uint64_t &nr, uint64_t &nc) {
+  std::string path = uri, query;
+  const size_t q = uri.find('?');
+  if (q != std::string::npos) path = uri.substr(0, q), query = uri.substr(q + 1);
+  const bool csv = query.find("format=csv") != std::string::npos;
+  long label_col = -1;
+  const size_t lc = query.find("label_column=");
+  if (lc != std::string::npos) label_col = strtol(query.c_str() + lc + 13, nullptr, 10);
+  FILE *fp = fopen(path.c_str(), "rb");
+  if (!fp) throw Error("Opening " + path + " failed");
+  std::string text;
+  char buf[1 << 16];
+  size_t n;
+  while ((n = fread(buf, 1, sizeof buf, fp)) > 0) text.append(buf, n);
+  fclose(fp);
+  std::vector<std::vector<std::pair<uint64_t, float>>> rows;
+  uint64_t maxcol = 0;
+  size_t pos = 0;
+  while (pos < text.size()) {
+    size_t eol = text.find('\n', pos);
+    if (eol == std::string::npos) eol = text.size();
+    std::string line = text.substr(pos, eol - pos);
+    pos = eol + 1;
+    if (!line.empty() && line.back() == '\r') line.pop_back();
+    if (line.find_first_not_of(" \t") == std::string::npos) continue;
+    std::vector<std::pair<uint64_t, float>> row;
+    const char *p = line.c_str();
+    if (csv) {
+      long col = 0;
+      uint64_t out_col = 0;
+      while (true) {
+        char *e = nullptr;
+        const float v = strtof(p, &e);
+        const bool empty = e == p;
+        if (col != label_col) {
+          if (!empty) row.emplace_back(out_col, v);
+          ++out_col;
+        }
+        p = e;
+        while (*p == ' ') ++p;
+        if (*p != ',') break;
+        ++p, ++col;
+      }
+      maxcol = std::max<uint64_t>(maxcol, out_col);
+    } else {
+      char *e = nullptr;
+      (void)strtof(p, &e);  // label
+      if (e == p) throw Error(path + ": not a libqcoh dense matrix file, and not libsvm text either");
+      p = e;
+      while (*p) {
+        while (*p == ' ' || *p == '\t') ++p;
+        if (!*p || *p == '#') break;
+        const uint64_t idx = strtoull(p, &e, 10);
+        if (e == p || *e != ':') throw Error(path + ": malformed libsvm entry");
+        p = e + 1;
+        const float v = strtof(p, &e);
+        if (e == p) throw Error(path + ": malformed libsvm value");
+        p = e;
+        row.emplace_back(idx, v);
+        maxcol = std::max<uint64_t>(maxcol, idx + 1);
+      }
+    }
+    rows.push_back(std::move(row));
+  }
+  nr = rows.size(), nc = maxcol;
+  h.assign((size_t)nr * nc, NAN);
+  for (uint64_t r = 0; r < nr; ++r)
+    for (auto &kv : rows[r]) h[(size_t)r * nc + kv.first] = kv.second;
+}
+
 int XGDMatrixCreateFromFile(const char *fname, int silent, DMatrixHandle *out) {
   (void)silent;
   std::vector<float> h;
   uint64_t nr = 0, nc = 0;
   float missing = NAN;
   try {
-    FILE *fp = fopen(fname, "rb");
-    if (!fp) throw Error(std::string("Opening ") + fname + " failed");
-    char magic[4];
-    uint32_t ver = 0;
-    bool ok = fread(magic, 1, 4, fp) == 4 && !memcmp(magic, "QCDM", 4) && fread(&ver, 4, 1, fp) == 1 && ver == 1 &&
-              fread(&nr, 8, 1, fp) == 1 && fread(&nc, 8, 1, fp) == 1 && fread(&missing, 4, 1, fp) == 1;
-    if (ok) {
-      h.resize((size_t)nr * nc);
-      ok = fread(h.data(), 4, h.size(), fp) == h.size();
+    if (!fname) throw Error("XGDMatrixCreateFromFile: fname is NULL");
+    const std::string uri(fname);
+    bool binary = false;
+    if (uri.find('?') == std::string::npos) {
+      FILE *fp = fopen(fname, "rb");
+      if (!fp) throw Error(std::string("Opening ") + fname + " failed");
+      char magic[4];
+      uint32_t ver = 0;
+      binary = fread(magic, 1, 4, fp) == 4 && !memcmp(magic, "QCDM", 4);
+      if (binary) {
+        bool ok = fread(&ver, 4, 1, fp) == 1 && ver == 1 && fread(&nr, 8, 1, fp) == 1 && fread(&nc, 8, 1, fp) == 1 &&
+                  fread(&missing, 4, 1, fp) == 1;
+        if (ok) {
+          h.resize((size_t)nr * nc);
+          ok = fread(h.data(), 4, h.size(), fp) == h.size();
+        }
+        if (!ok) {
+          fclose(fp);
+          throw Error(std::string(fname) + ": truncated libqcoh dense matrix file");
+        }
+      }
+      fclose(fp);
     }
-    fclose(fp);
-    if (!ok) throw Error(std::string(fname) + ": not a libqcoh dense matrix file (XGBoost's own binary DMatrix, libsvm and csv inputs are not supported)");
+    // XGBoost's own binary DMatrix container is not read; anything else is tried as libsvm / csv text
+    if (!binary) parse_text_matrix(uri, h, nr, nc);
   } catch (const std::exception &e) {
     g_err = e.what();
     return -1;

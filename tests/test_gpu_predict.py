@@ -297,6 +297,30 @@ def test_dmatrix_file_roundtrip(capi, tmp_path, small_model_path):
     assert np.array_equal(b.predict(d), b.predict(d2))
 
 
+def test_dmatrix_from_libsvm_and_csv(capi, oracle, tmp_path, small_model_path):
+    """XGDMatrixCreateFromFile's text inputs: libsvm (absent entries are missing) and csv with a label column."""
+    rng = np.random.default_rng(4)
+    x = synth.quick_features(synth.raw_fields(4))[:300]
+    x[rng.random(x.shape) < 0.1] = np.nan
+    svm, csv = tmp_path / "x.libsvm", tmp_path / "x.csv"
+    with open(svm, "w") as f:
+        for r in x:
+            f.write("0 " + " ".join(f"{j}:{float(v)!r}" for j, v in enumerate(r) if not np.isnan(v)) + "\n")
+    with open(csv, "w") as f:
+        for r in x:
+            f.write("1.5," + ",".join("" if np.isnan(v) else repr(float(v)) for v in r) + "\n")
+    x[:, -1] = np.where(np.isnan(x[:, -1]), x[:, -1], x[:, -1])  # (libsvm infers ncol from the largest index)
+    ref = oracle.Model(small_model_path).predict(x, missing=np.nan)
+    b = capi.Booster(small_model_path)
+    d1 = capi.DMatrix.from_file(str(svm))
+    d2 = capi.DMatrix.from_file(str(csv) + "?format=csv&label_column=0")
+    assert d2.num_row == 300 and d2.num_col == 27 and d1.num_row == 300 and d1.num_col <= 27
+    assert np.array_equal(b.predict(d1).view(np.uint32), ref.view(np.uint32))
+    assert np.array_equal(b.predict(d2).view(np.uint32), ref.view(np.uint32))
+    with pytest.raises(capi.QcohError):
+        capi.DMatrix.from_file(str(tmp_path / "missing_file.libsvm"))
+
+
 def test_linearity_property_full_size(capi, small_model_path):
     """Size-independent property at a BASELINE-sized slab (C90 x 72 = 3.5 M rows): predicting the
     matrix in one call equals predicting its halves (rows are independent), and a permutation of
