@@ -2,6 +2,7 @@
 // owning buffers, handle types.  Internal; nothing here is exported.
 #pragma once
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>  // header-only; a no-op unless a profiler is attached
 
 #include <algorithm>
 #include <cmath>
@@ -35,7 +36,14 @@ struct Error : std::runtime_error {
                   cudaGetErrorString(e__));                                                           \
   } while (0)
 
-#define API_BEGIN try {
+// every C ABI entry point is an NVTX range named after the function (visible in Nsight Systems / ncu)
+struct NvtxRange {
+  explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+};
+#define API_BEGIN        \
+  NvtxRange nvtx__(__func__); \
+  try {
 #define API_END                      \
   }                                  \
   catch (const std::exception &e) {  \
