@@ -121,6 +121,20 @@ def test_save_model_roundtrip_all_formats(capi, tmp_path):
             assert np.array_equal(nt.left, t.left) and np.array_equal(nt.split_cond, t.split_cond)
 
 
+def test_json_loader_is_whitespace_and_signed_zero_safe(capi, tmp_path):
+    import json
+
+    f = synth.random_forest_structure(3, 4, seed=2)
+    f.trees[0].split_cond[0] = np.float32(-0.0)
+    f.trees[1].split_cond[0] = np.float32(1e-45)  # denormal threshold survives the text round trip
+    xgbmodel.write_json(f, str(tmp_path / "compact.json"))
+    open(tmp_path / "pretty.json", "w").write(json.dumps(xgbmodel.forest_to_jsonable(f), indent=2))
+    a = capi.Booster(str(tmp_path / "compact.json"), parse_only=True).flat()
+    b = capi.Booster(str(tmp_path / "pretty.json"), parse_only=True).flat()
+    assert all(np.array_equal(x, y) for x, y in zip(a, b))
+    assert a[0][0, 0] == 0x80000000 and a[0][int(a[1][1]), 0] == 1
+
+
 def test_loader_rejects_bad_models(capi, tmp_path):
     f = synth.random_forest_structure(2, 3, seed=1)
     cases = {}
