@@ -73,7 +73,11 @@ cudaError_t launch_fill(float *p, uint64_t n, float v, cudaStream_t s) {
 // XGBoost semantics restated (xgboost 1.6.0 src/predictor/predict_fn.h GetNextNode,
 // src/predictor/cpu_predictor.cc PredictByAllTrees): missing -> default child, else
 // left + !(fvalue < split_cond); out = base_score, then += leaf value tree by tree in float32.
-constexpr int kBlock = 256;  // rows per CTA; the feature stride in the transposed tile is kBlock floats
+#ifndef QC_BLOCK
+#define QC_BLOCK 256
+#endif
+constexpr int kBlock = QC_BLOCK;  // rows (= threads) per CTA
+constexpr int kStride = 256;      // feature stride of the transposed tile, in floats (1 KB: the PRMT address trick)
 
 // Order-preserving integer keys.  The tile and the device copy of the nodes do not hold floats but
 // key(v) = bits ^ (sign ? 0xFFFFFFFF : 0x80000000) of the value with -0.0 folded into +0.0, which is
@@ -141,7 +145,7 @@ __device__ __forceinline__ void walk_group(const uint2 *__restrict__ nodes, cuda
   auto visit = [&](int j) {
     // shared address of srow[feat][tid] = my_saddr + feat * (kBlock * 4): the top byte of the meta word
     // is feat * 4, so moving it to byte 1 (one PRMT) gives feat * 1024
-    static_assert(kBlock * 4 == 1024 && kMetaFeatShift == 26, "address trick assumes a 1 KB feature stride");
+    static_assert(kStride * 4 == 1024 && kBlock <= kStride && kMetaFeatShift == 26, "address trick assumes a 1 KB feature stride");
     const uint32_t sa = my_saddr + __byte_perm(nd[j].y, 0u, 0x4434);
     uint32_t kv;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(kv) : "r"(sa));
@@ -283,11 +287,11 @@ __global__ void __launch_bounds__(kBlock, MINB) predict_rows_kernel(DeviceForest
         const float x = v[c];
         uint32_t k = float_key(x);
         if (HAS_MISSING && (x != x || x == a.missing)) k = kKeyMissing;
-        skey[c * B + tid] = k;
+        skey[c * kStride + tid] = k;
       }
     // columns the matrix does not have are missing (xgboost FVec::Fill leaves them flagged)
-    for (int c = nc32; c < f.nfeat; ++c) skey[c * B + tid] = kKeyMissing;
-    skey[f.nfeat * B + tid] = 0u;
+    for (int c = nc32; c < f.nfeat; ++c) skey[c * kStride + tid] = kKeyMissing;
+    skey[f.nfeat * kStride + tid] = 0u;
   }
   if (tid >= nr) return;
   const bool live = true;
@@ -367,13 +371,13 @@ __global__ void __launch_bounds__(kBlock, 6) predict_soa_kernel(DeviceForest f, 
       uint32_t k = float_key(x);
       if (x != x || x == a.missing) k = kKeyMissing, flags |= 1;
       if (chk_inf && isinf(x)) flags |= 2;
-      skey[ft * B + tid] = k;
+      skey[ft * kStride + tid] = k;
     }
   } else {
 #pragma unroll
-    for (int ft = 0; ft < 27; ++ft) skey[ft * B + tid] = 0u;
+    for (int ft = 0; ft < 27; ++ft) skey[ft * kStride + tid] = 0u;
   }
-  skey[27 * B + tid] = 0u;  // the slot leaves point at (nfeat == 27 is checked by the host)
+  skey[27 * kStride + tid] = 0u;  // the slot leaves point at (nfeat == 27 is checked by the host)
   // __syncthreads_or returns a truth value, not the bitwise OR: one vote per flag
   const bool tile_missing = __syncthreads_or(flags & 1) != 0;
   if (__syncthreads_or(flags & 2) != 0) {
@@ -393,7 +397,7 @@ __global__ void __launch_bounds__(kBlock, 6) predict_soa_kernel(DeviceForest f, 
 cudaError_t launch_predict_soa(const DeviceForest &f, const SoaArgs &a, const Tunables &t, cudaStream_t s) {
   if (a.nrow == 0) return cudaSuccess;
   if (f.nfeat != 27) return cudaErrorInvalidValue;
-  const size_t smem = (size_t)kBlock * 28 * sizeof(float);
+  const size_t smem = (size_t)kStride * 28 * sizeof(float);
   const uint64_t nblk = (a.nrow + kBlock - 1) / kBlock;
   if (nblk > 0x7fffffffull) return cudaErrorInvalidConfiguration;
   const bool tex = f.tex != 0 && t.variant >= 0;
@@ -408,7 +412,7 @@ template <int ILP, bool HM, bool PL, bool PARK, int MINB, int TEXMODE = 0, int C
 static cudaError_t launch_predict_one(const DeviceForest &f, const PredictArgs &a, cudaStream_t s) {
   // srow holds max(ncol, nfeat + 1) feature slots per thread
   const int slots = (f.nfeat + 1) > a.ncol ? (f.nfeat + 1) : a.ncol;
-  const size_t smem = (size_t)kBlock * slots * sizeof(float);
+  const size_t smem = (size_t)kStride * slots * sizeof(float);
   const uint64_t nblk = (a.nrow + kBlock - 1) / kBlock;
   if (nblk > 0x7fffffffull) return cudaErrorInvalidConfiguration;
   auto k = predict_rows_kernel<ILP, HM, PL, PARK, MINB, TEXMODE, CTOP>;
