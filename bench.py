@@ -212,6 +212,11 @@ def main():
         booster_path()
     if dist:
         dist.barrier()
+        # the library's own NCCL communicator for the diagnostic all-reduce: rank 0's id travels over the
+        # process group (a MAPL host would MPI_Bcast it)
+        uid = [capi.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        capi.comm_init(world, rank, uid[0])
     booster = capi.Booster(booster_path())
     info = booster.info()
 
@@ -277,13 +282,12 @@ def main():
     value = total_cells / (ms_step * 1e-3)
 
     # ---- run1: fused device-resident Run1 (+ NCCL all-reduce of the diagnostic at N > 1)
-    diag_t = torch.zeros(4, dtype=torch.float64, device="cuda") if dist else None
+    diag_sum = [list(ro.diag)]
 
     def run1_step():
         capi.check(L.qcoh_oh_run1(oh.handle, capi.C.byref(rin), capi.C.byref(ro)))
-        if dist:
-            diag_t.copy_(torch.tensor(list(ro.diag), dtype=torch.float64))
-            dist.all_reduce(diag_t)
+        if dist:  # ncclAllReduce(sum, float64, count = 4) inside libqcoh, over NVLink / NVSwitch
+            diag_sum[0] = capi.comm_allreduce_sum(list(ro.diag)).tolist()
 
     def wall(fn, steps, warm):
         for _ in range(warm):
@@ -298,7 +302,7 @@ def main():
         return max_over_ranks(dt) / steps
 
     ms_run1 = wall(run1_step, max(3, args.steps // 2), 2)
-    diag = list(ro.diag) if not dist else diag_t.tolist()
+    diag = list(ro.diag) if not dist else diag_sum[0]
 
     # ---- e2e: xgb_fortran_api C ABI from pinned host buffers
     e2e = None
@@ -355,6 +359,7 @@ def main():
 
     if rank != 0:
         if dist:
+            capi.comm_destroy()
             dist.destroy_process_group()
         return
     peaks = {}
@@ -392,6 +397,7 @@ def main():
     }  # fmt: skip
     print(json.dumps(out), flush=True)
     if dist:
+        capi.comm_destroy()
         dist.destroy_process_group()
 
 

@@ -86,6 +86,25 @@ module qcoh_fortran_api
        integer(c_int64_t)        :: col0, ncol_local
      end function
 
+     ! NCCL all-reduce of the diagnostic partial sums: rank 0 gets the id, MPI_Bcast it, every rank joins
+     integer(c_int) function qcoh_comm_get_unique_id(id) bind(C, name="qcoh_comm_get_unique_id")
+       import :: c_int, c_char
+       character(len=1, kind=c_char), dimension(128) :: id
+     end function
+     integer(c_int) function qcoh_comm_init(nranks, rank, id) bind(C, name="qcoh_comm_init")
+       import :: c_int, c_char
+       integer(c_int), value :: nranks, rank
+       character(len=1, kind=c_char), dimension(128) :: id
+     end function
+     integer(c_int) function qcoh_comm_allreduce_sum_f64(values, n) bind(C, name="qcoh_comm_allreduce_sum_f64")
+       import :: c_int, c_double
+       real(c_double), dimension(*) :: values
+       integer(c_int), value :: n
+     end function
+     integer(c_int) function qcoh_comm_destroy() bind(C, name="qcoh_comm_destroy")
+       import :: c_int
+     end function
+
      function XGBGetLastError_c() bind(C, name="XGBGetLastError") result(msg)
        import :: c_ptr
        type(c_ptr) :: msg

@@ -220,6 +220,16 @@ int qcoh_predict_OH_with_XGB(const char *xgb_fname, int icount, int jcount, int 
 /* Drop the static booster of the mirror (tests). */
 void qcoh_predict_OH_reset(void);
 
+/* ---- the one collective: all-reduce of the diagnostic partial sums over NCCL ------------- */
+/* One process per GPU.  Rank 0 obtains a 128-byte id and hands it to the others (MPI_Bcast in a MAPL host);
+ * every rank then joins.  libnccl.so.2 is dlopen'ed on first use (no link-time dependency).  The data path
+ * needs none of this: cells shard with no halo. */
+int qcoh_comm_get_unique_id(char id[128]);
+int qcoh_comm_init(int nranks, int rank, const char id[128]);
+/* In-place sum over all ranks of n float64 values in host memory (qcoh_run1_out.diag: n = 4). */
+int qcoh_comm_allreduce_sum_f64(double *values, int n);
+int qcoh_comm_destroy(void);
+
 /* ---- sharding across GPUs -------------------------------------------- */
 /* Contiguous, near-equal split of `ncol_global` columns over `nranks`; no halo. */
 int qcoh_partition_columns(int64_t ncol_global, int nranks, int rank, int64_t *col0, int64_t *ncol_local);

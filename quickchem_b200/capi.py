@@ -70,7 +70,8 @@ QCOH_SYMBOLS = ("qcoh_version", "qcoh_device_count", "qcoh_set_device", "qcoh_ho
                 "qcoh_dmatrix_create_device", "qcoh_dmatrix_device_ptr", "qcoh_dmatrix_upload", "qcoh_dmatrix_seal",
                 "qcoh_booster_predict_device", "qcoh_set_param", "qcoh_launch_count", "qcoh_oh_create",
                 "qcoh_oh_run1", "qcoh_oh_free", "qcoh_oh_get_diag", "qcoh_predict_OH_with_XGB", "qcoh_predict_OH_reset",
-                "qcoh_partition_columns")  # fmt: skip
+                "qcoh_partition_columns", "qcoh_comm_get_unique_id", "qcoh_comm_init",
+                "qcoh_comm_allreduce_sum_f64", "qcoh_comm_destroy")  # fmt: skip
 
 _LIB = None
 
@@ -121,6 +122,9 @@ def lib():
         L.qcoh_predict_OH_with_XGB.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, vp, vp,
                                                C.POINTER(vp), C.POINTER(C.c_int), vp]  # fmt: skip
         L.qcoh_partition_columns.argtypes = [C.c_int64, C.c_int, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+        L.qcoh_comm_get_unique_id.argtypes = [C.c_char_p]
+        L.qcoh_comm_init.argtypes = [C.c_int, C.c_int, C.c_char_p]
+        L.qcoh_comm_allreduce_sum_f64.argtypes = [C.POINTER(C.c_double), C.c_int]
         _LIB = L
     return _LIB
 
@@ -150,6 +154,27 @@ def partition_columns(ncol_global: int, nranks: int, rank: int):
     c0, n = C.c_int64(), C.c_int64()
     check(lib().qcoh_partition_columns(ncol_global, nranks, rank, C.byref(c0), C.byref(n)))
     return c0.value, n.value
+
+
+def comm_unique_id() -> bytes:
+    buf = C.create_string_buffer(128)
+    check(lib().qcoh_comm_get_unique_id(buf))
+    return buf.raw
+
+
+def comm_init(nranks: int, rank: int, uid: bytes) -> None:
+    check(lib().qcoh_comm_init(nranks, rank, uid))
+
+
+def comm_allreduce_sum(values) -> np.ndarray:
+    """NCCL all-reduce (sum) of a few float64 values, in the library, without torch."""
+    a = np.ascontiguousarray(values, np.float64).copy()
+    check(lib().qcoh_comm_allreduce_sum_f64(a.ctypes.data_as(C.POINTER(C.c_double)), a.size))
+    return a
+
+
+def comm_destroy() -> None:
+    check(lib().qcoh_comm_destroy())
 
 
 def _ptr(a):

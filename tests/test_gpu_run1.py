@@ -214,3 +214,21 @@ def test_host_mirror_predict_OH_with_XGB(capi, oracle, small_model_path):
                                     fields["TROPP"], bb, OH2) == 0  # fmt: skip
     assert np.array_equal(OH_ML, OH2)
     capi.lib().qcoh_predict_OH_reset()
+
+
+def test_native_nccl_allreduce_single_rank(capi):
+    """qcoh_comm_*: the library's own NCCL communicator (dlopen'ed libnccl).  One GPU here, so one rank: the
+    all-reduce must be the identity; bench.py --gpus N exercises N ranks."""
+    uid = capi.comm_unique_id()
+    assert len(uid) == 128
+    capi.comm_init(1, 0, uid)
+    try:
+        v = np.array([1.5, -2.25, 3e300, 4e-300])
+        assert np.array_equal(capi.comm_allreduce_sum(v), v)
+        with pytest.raises(capi.QcohError, match="already exists"):
+            capi.comm_init(1, 0, uid)
+    finally:
+        capi.comm_destroy()
+    with pytest.raises(capi.QcohError, match="qcoh_comm_init first"):
+        capi.comm_allreduce_sum([1.0])
+
