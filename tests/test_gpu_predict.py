@@ -297,6 +297,22 @@ def test_dmatrix_file_roundtrip(capi, tmp_path, small_model_path):
     assert np.array_equal(b.predict(d), b.predict(d2))
 
 
+def test_more_trees_than_the_constant_table_holds(capi, oracle, tmp_path):
+    """The constant-memory table of tree tops holds 8000 nodes (500 trees x 16); a bigger forest must run
+    without it and still match."""
+    rng = np.random.default_rng(8)
+    trees = [xgbmodel.tree_from_nested((int(rng.integers(27)), float(rng.normal()), bool(rng.random() < 0.5),
+                                        float(rng.normal()), (int(rng.integers(27)), float(rng.normal()), False, 1.0, -1.0)))
+             for _ in range(650)]  # fmt: skip
+    f = xgbmodel.Forest(trees=trees, base_score=0.25, num_feature=27)
+    x = rng.normal(0, 1, (3000, 27)).astype(np.float32)
+    got, ref = _both(capi, oracle, f, x, tmp_path)
+    assert np.array_equal(got.view(np.uint32), ref.view(np.uint32))
+    x[::3, 5] = np.nan
+    got, ref = _both(capi, oracle, f, x, tmp_path)
+    assert np.array_equal(got.view(np.uint32), ref.view(np.uint32))
+
+
 def test_dmatrix_from_libsvm_and_csv(capi, oracle, tmp_path, small_model_path):
     """XGDMatrixCreateFromFile's text inputs: libsvm (absent entries are missing) and csv with a label column."""
     rng = np.random.default_rng(4)
