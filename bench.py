@@ -362,6 +362,10 @@ def main():
             capi.comm_destroy()
             dist.destroy_process_group()
         return
+    # compute-side view of the same kernel: node visits per second (SURVEY.md 8d "compute-side bound")
+    xs_v = np.empty((4096, NFEAT), np.float32)
+    capi.check(L.qcoh_memcpy_d2h(xs_v.ctypes.data_as(capi.vp), xptr, xs_v.nbytes))
+    visits = capi.node_visits_per_cell(booster, xs_v)
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -386,6 +390,9 @@ def main():
                      "frac": achieved / peak, "traffic": traffic, "traffic_unit": "bytes/launch", "traffic_source": traffic_src,
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured copy)" if peaks else "fallback 6.65 TB/s",
                      "algorithmic_bytes_per_cell": ALGO_BYTES_PER_CELL, "cells_per_launch": ncell,
+                     "compute_side": {"node_visits_per_cell": round(visits, 1), "node_visits_per_s_per_gpu": ncell * visits / (ms_step * 1e-3),
+                                      "note": "one visit = one 8-byte node gather + one feature fetch + compare; "
+                                              "12.75 SASS instructions per visit, issue slots 78 % busy (profiles/README.md)"},
                      "note": "traversal is bound by the L1TEX data pipe (node gathers), not HBM: ncu l1tex 92 %, DRAM 1.3 % (profiles/README.md)"},
         "cpu_baseline": cpu,
         "run1": {"value": total_cells / (ms_run1 * 1e-3), "unit": "cells/s", "ms_per_step": ms_run1,

@@ -345,6 +345,25 @@ class Booster:
             pass
 
 
+def node_visits_per_cell(booster: "Booster", x_sample: np.ndarray) -> float:
+    """Mean number of node fetches per row (sum over trees of leaf depth + 1), from the device's own per-tree
+    leaf ids on a sample of rows and the flattened (depth-ordered) layout."""
+    leaf = booster.predict(DMatrix(x_sample), option_mask=2).astype(np.int64)
+    nodes, off, _, orig = booster.flat()
+    visits = 0.0
+    for t in range(len(off) - 1):
+        n0, n1 = int(off[t]), int(off[t + 1])
+        rel = (nodes[n0:n1, 1] & ((1 << 23) - 1)).astype(np.int64)
+        dep = np.zeros(n1 - n0, np.int32)
+        for i in np.nonzero(rel)[0]:  # breadth-first order: parents come before their children
+            dep[i + rel[i]] = dep[i] + 1
+            dep[i + rel[i] + 1] = dep[i] + 1
+        lut = np.empty(n1 - n0, np.int64)
+        lut[orig[n0:n1]] = np.arange(n1 - n0)
+        visits += float(dep[lut[leaf[:, t]]].mean()) + 1.0
+    return visits
+
+
 def synchronize():
     check(lib().qcoh_device_synchronize())
 

@@ -59,20 +59,7 @@ for (t, d), p in paths.items():
     for _ in range(n):
         b.predict_device(dX, out, exp10=True, scale=0.85)
     ms = capi.timer_stop() / n
-    # mean visited depth from leaf ids of a sample (device leaf-index output)
-    leaf = b.predict(capi.DMatrix(hx[:4096]), option_mask=2).astype(np.int64)
-    nodes, off, depth, orig = b.flat()
-    pos = np.empty(int(off[-1]), np.int64)
-    visits = 0.0
-    for ti in range(info.num_trees):
-        n0, n1 = int(off[ti]), int(off[ti + 1])
-        meta = nodes[n0:n1, 1]; rel = (meta & ((1 << 23) - 1)).astype(np.int64)
-        dep = np.zeros(n1 - n0, np.int32)
-        idx = np.nonzero(rel)[0]
-        for i in idx:  # BFS order: parents before children
-            dep[i + rel[i]] = dep[i] + 1; dep[i + rel[i] + 1] = dep[i] + 1
-        lut = np.empty(n1 - n0, np.int64); lut[orig[n0:n1]] = np.arange(n1 - n0)
-        visits += dep[lut[leaf[:, ti]]].mean() + 1
+    visits = capi.node_visits_per_cell(b, hx[:4096])
     gbs = ncell * 112 / 1e9 / (ms * 1e-3)
     rows.append(dict(trees=t, max_depth=d, nodes=int(info.num_nodes), visits_per_cell=round(visits, 1), ms=round(ms, 3),
                      cells_per_s=ncell / (ms * 1e-3), hbm_gbs=round(gbs, 1), hbm_frac=round(gbs / peak, 4)))
