@@ -247,6 +247,8 @@ struct UbjReader {
           if (marker() != '#') fail("UBJSON model: typed array without count");
           int64_t n = integer(marker());
           if (n < 0) fail("UBJSON model: negative array length");
+          const size_t elem = ty == 'D' || ty == 'L' ? 8 : ty == 'd' || ty == 'l' ? 4 : ty == 'I' ? 2 : 1;
+          if ((uint64_t)n > (uint64_t)(end - p) / elem) fail("UBJSON model: typed array longer than the file");
           if (ty == 'd' || ty == 'D') {
             v.kind = JV::F32A;
             v.f32a.resize((size_t)n);
