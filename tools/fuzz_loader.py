@@ -1,5 +1,7 @@
-import numpy as np, os, sys, tempfile, subprocess
-sys.path.insert(0,'/root/repo')
+"""Mutate model files (truncate / flip / insert / overwrite length fields) and feed them to the loaders: every
+file must be accepted or rejected with an error, never crash.  python tools/fuzz_loader.py [seed] [iterations]"""
+import numpy as np, os, sys, tempfile
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from quickchem_b200 import capi, synth, xgbmodel
 f = synth.random_forest_structure(3, 4, seed=2)
 d = tempfile.mkdtemp()
