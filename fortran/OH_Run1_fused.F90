@@ -41,6 +41,13 @@
 !      first_time = .FALSE.
 !   END IF ONE_TIME_SETUP
 !
+!   ! optional, off by default (new rc key `reload_model_on_month_change: F`): follow the %m2 of the file
+!   ! pattern instead of keeping the start month's booster for the whole run (reference behaviour, :182,209)
+!   IF ( need_to_call_BOOST .AND. self%reload_model_on_month_change ) THEN
+!      rc = qcoh_oh_select_model( oh_dev, TRIM(self%XGBoostFilePattern)//c_null_char, nymd, nhms, changed )
+!      _ASSERT(rc==0, qcoh_last_error())
+!   END IF
+!
 !   rin%nymd = nymd
 !   rin%need_to_call_boost = merge(1, 0, need_to_call_BOOST)
 !   rin%T_MOD   = c_loc(T_MOD)   ;  rin%Q_MOD  = c_loc(Q_MOD)
@@ -62,6 +69,7 @@
 !   CALL MAPL_GetPointer(export, ptr3d, 'DIAG_NDWET', __RC__)
 !   IF (ASSOCIATED(ptr3d)) rout%NDWET = c_loc(ptr3d)                 ! (:1598-1599)
 !   rout%X = c_null_ptr ;  rout%pred = c_null_ptr
+!   rout%LOSS_CH4 = c_null_ptr ;  rout%LOSS_CO = c_null_ptr          ! or c_loc of a new export, for CH4 / CO
 !
 !   rc = qcoh_oh_run1( oh_dev, rin, rout )
 !   _ASSERT(rc==0, qcoh_last_error())      ! carries 'Minimum tropopause pressure is not low enough!' (:288)

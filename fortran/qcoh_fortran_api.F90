@@ -41,6 +41,7 @@ module qcoh_fortran_api
 
   type, bind(C) :: qcoh_run1_out
      type(c_ptr) :: OH, OH_boost, NDWET, X, pred   ! c_null_ptr = not wanted
+     type(c_ptr) :: LOSS_CH4, LOSS_CO              ! k(T)[OH] in 1/s for the CH4 / CO consumers (build-defined)
      integer(c_int) :: k1
      real(c_double) :: diag(4)
   end type qcoh_run1_out
@@ -76,6 +77,36 @@ module qcoh_fortran_api
      integer(c_int) function qcoh_oh_free(h) bind(C, name="qcoh_oh_free")
        import :: c_int, c_ptr
        type(c_ptr), value :: h
+     end function
+
+     ! Opt-in month roll-over (the reference keeps the first month's booster for the whole run,
+     ! OH_GridCompMod.F90:182,209,1187): pattern = self%XGBoostFilePattern//c_null_char; expands the
+     ! template, takes the booster of that file from the process-wide cache and switches the handle to it.
+     integer(c_int) function qcoh_oh_select_model(h, pattern, nymd, nhms, changed) bind(C, name="qcoh_oh_select_model")
+       import :: c_int, c_ptr, c_char
+       type(c_ptr), value :: h
+       character(len=1, kind=c_char), dimension(*) :: pattern
+       integer(c_int), value :: nymd, nhms
+       integer(c_int)        :: changed
+     end function
+
+     integer(c_int) function qcoh_oh_set_booster(h, booster) bind(C, name="qcoh_oh_set_booster")
+       import :: c_int, c_ptr
+       type(c_ptr), value :: h, booster
+     end function
+
+     integer(c_int) function qcoh_model_cache_get(fname, out) bind(C, name="qcoh_model_cache_get")
+       import :: c_int, c_ptr, c_char
+       character(len=1, kind=c_char), dimension(*) :: fname
+       type(c_ptr) :: out   ! BoosterHandle*, owned by the cache
+     end function
+
+     integer(c_int) function qcoh_expand_template(pattern, nymd, nhms, out, cap) bind(C, name="qcoh_expand_template")
+       import :: c_int, c_char, c_size_t
+       character(len=1, kind=c_char), dimension(*) :: pattern
+       integer(c_int), value    :: nymd, nhms
+       character(len=1, kind=c_char), dimension(*) :: out
+       integer(c_size_t), value :: cap
      end function
 
      integer(c_int) function qcoh_partition_columns(ncol_global, nranks, rank, col0, ncol_local) &

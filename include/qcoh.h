@@ -193,6 +193,12 @@ typedef struct {
   float *NDWET;     /* [km][ncol] — export DIAG_NDWET (:1598-1599) */
   float *X;         /* [ncol*ksub][27] assembled feature matrix (debug / parity) */
   float *pred;      /* [ncol*ksub] raw booster output (debug / parity) */
+  /* SURVEY.md 8(f)4 — what the consumers of OH need next (the parent re-exports OH for the CH4 / CO
+   * chemistry, QuickChem_GridCompMod.F90:184-185; comment OH_GridCompMod.F90:1590-1591).  Build-defined,
+   * not in the reference: first-order loss frequencies [km][ncol] in 1/s from the final OH (molec/cm3),
+   *   LOSS_CH4 = 2.45e-12 exp(-1775 / T_MOD) * OH        (JPL 19-5, OH + CH4)
+   *   LOSS_CO  = 1.5e-13 (1 + 0.6 PL_MOD / 101325) * OH  (OH + CO, pressure-dependent form) */
+  float *LOSS_CH4, *LOSS_CO;
   int k1;           /* out: first predicted level, 1-based (k2 = km), :300-301 */
   /* build-defined diagnostic, local partial sums (float64): sum(OH*w), sum(w),
    * sum(nCH4*V), sum(k(T)*OH*nCH4*V); valid when AREA != NULL */
@@ -202,6 +208,30 @@ typedef struct {
 int qcoh_oh_create(BoosterHandle booster, const qcoh_oh_config *cfg, qcoh_oh_handle *out);
 int qcoh_oh_run1(qcoh_oh_handle h, const qcoh_run1_in *in, qcoh_run1_out *out);
 int qcoh_oh_free(qcoh_oh_handle h);
+/* Replace the booster a fused-Run1 handle predicts with (27 features required).  The persistent OH_ML of
+ * the previous boost step stays valid.  The booster must outlive the handle. */
+int qcoh_oh_set_booster(qcoh_oh_handle h, BoosterHandle booster);
+int qcoh_oh_get_booster(qcoh_oh_handle h, BoosterHandle *out);
+
+/* ---- monthly model files -------------------------------------- */
+/* The reference expands `XGBoostFile: ..._M%m2.model` (OH_instance_OH.rc:20) with fill_grads_template on
+ * every Run1 (OH_GridCompMod.F90:1187) but its SAVE'd booster is loaded once (:182,209,242-271), so a
+ * month roll-over keeps predicting with the start month's model.  libqcoh keeps that behaviour unless the
+ * host opts in with the three calls below.
+ *
+ * GrADS-style expansion of the tokens %y4 %y2 %m1 %m2 %mc %Mc %MC %d1 %d2 %h1 %h2 %n2 %j3 (%% = '%');
+ * nymd = yyyymmdd, nhms = hhmmss.  Fails on an unknown token or when `cap` (including the NUL) is too small. */
+int qcoh_expand_template(const char *pattern, int nymd, int nhms, char *out, size_t cap);
+/* Process-wide cache of parsed + uploaded boosters keyed by file name: the first request for a name loads
+ * it, later ones return the same handle.  Handles belong to the cache (XGBoosterFree on one fails); a month
+ * of the production forest is ~20 MB of HBM, so all twelve stay resident. */
+int qcoh_model_cache_get(const char *fname, BoosterHandle *out);
+int qcoh_model_cache_size(void);
+/* Frees every cached booster; handles obtained from the cache (and fused-Run1 handles using them) die. */
+int qcoh_model_cache_clear(void);
+/* expand + cache_get + qcoh_oh_set_booster in one call: what a patched Run1 calls before a boost step when
+ * `reload_model_on_month_change` is on.  *changed (may be NULL) is set to 1 when the booster was switched. */
+int qcoh_oh_select_model(qcoh_oh_handle h, const char *pattern, int nymd, int nhms, int *changed);
 /* Diagnostic exports (OH_GridCompMod.F90:1602-1735, OH_StateSpecs.rc:41-73): copy one derived field of
  * the last boost step out of HBM.  name (case-sensitive, the DIAG_ suffix of the reference's export):
  * 3-D [km][ncol]: "TAUCLWDN" "TAUCLIDN" "TAUCLIUP" "TAUCLWUP" "AODUP" "AODDN" "PL" (PL_MOD, Pa) "NDWET"
@@ -219,6 +249,9 @@ int qcoh_predict_OH_with_XGB(const char *xgb_fname, int icount, int jcount, int 
                              const float *const bb[27], const int is2d[27], float *OH_ML);
 /* Drop the static booster of the mirror (tests). */
 void qcoh_predict_OH_reset(void);
+/* on != 0: the mirror calls XGBoosterLoadModel again whenever xgb_fname differs from the file its static
+ * booster was loaded from (fixes SURVEY.md 0.5); default 0 = the reference's load-once behaviour. */
+void qcoh_predict_OH_reload_on_file_change(int on);
 
 /* ---- the one collective: all-reduce of the diagnostic partial sums over NCCL ------------- */
 /* One process per GPU.  Rank 0 obtains a 128-byte id and hands it to the others (MPI_Bcast in a MAPL host);

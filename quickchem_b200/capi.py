@@ -55,7 +55,8 @@ class Run1In(C.Structure):
 
 
 class Run1Out(C.Structure):
-    _fields_ = [("OH", vp), ("OH_boost", vp), ("NDWET", vp), ("X", vp), ("pred", vp), ("k1", C.c_int),
+    _fields_ = [("OH", vp), ("OH_boost", vp), ("NDWET", vp), ("X", vp), ("pred", vp),
+                ("LOSS_CH4", vp), ("LOSS_CO", vp), ("k1", C.c_int),
                 ("diag", C.c_double * 4)]  # fmt: skip
 
 
@@ -70,6 +71,9 @@ QCOH_SYMBOLS = ("qcoh_version", "qcoh_device_count", "qcoh_set_device", "qcoh_ho
                 "qcoh_dmatrix_create_device", "qcoh_dmatrix_device_ptr", "qcoh_dmatrix_upload", "qcoh_dmatrix_seal",
                 "qcoh_booster_predict_device", "qcoh_set_param", "qcoh_launch_count", "qcoh_oh_create",
                 "qcoh_oh_run1", "qcoh_oh_free", "qcoh_oh_get_diag", "qcoh_predict_OH_with_XGB", "qcoh_predict_OH_reset",
+                "qcoh_predict_OH_reload_on_file_change", "qcoh_oh_set_booster", "qcoh_oh_get_booster",
+                "qcoh_expand_template", "qcoh_model_cache_get", "qcoh_model_cache_size", "qcoh_model_cache_clear",
+                "qcoh_oh_select_model",
                 "qcoh_partition_columns", "qcoh_comm_get_unique_id", "qcoh_comm_init",
                 "qcoh_comm_allreduce_sum_f64", "qcoh_comm_destroy")  # fmt: skip
 
@@ -125,6 +129,13 @@ def lib():
         L.qcoh_comm_get_unique_id.argtypes = [C.c_char_p]
         L.qcoh_comm_init.argtypes = [C.c_int, C.c_int, C.c_char_p]
         L.qcoh_comm_allreduce_sum_f64.argtypes = [C.POINTER(C.c_double), C.c_int]
+        L.qcoh_oh_set_booster.argtypes = [vp, vp]
+        L.qcoh_oh_get_booster.argtypes = [vp, C.POINTER(vp)]
+        L.qcoh_expand_template.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_char_p, C.c_size_t]
+        L.qcoh_model_cache_get.argtypes = [C.c_char_p, C.POINTER(vp)]
+        L.qcoh_oh_select_model.argtypes = [vp, C.c_char_p, C.c_int, C.c_int, C.POINTER(C.c_int)]
+        L.qcoh_predict_OH_reload_on_file_change.argtypes = [C.c_int]
+        L.qcoh_predict_OH_reload_on_file_change.restype = None
         _LIB = L
     return _LIB
 
@@ -278,9 +289,28 @@ class DMatrix:
             pass
 
 
+def expand_template(pattern: str, nymd: int, nhms: int = 0) -> str:
+    """fill_grads_template for the XGBoostFile pattern (OH_GridCompMod.F90:1187, OH_instance_OH.rc:20)."""
+    buf = C.create_string_buffer(4096)
+    check(lib().qcoh_expand_template(os.fsencode(pattern), nymd, nhms, buf, C.c_size_t(len(buf))))
+    return os.fsdecode(buf.value)
+
+
+def model_cache_size() -> int:
+    return int(lib().qcoh_model_cache_size())
+
+
+def model_cache_clear() -> None:
+    check(lib().qcoh_model_cache_clear())
+
+
 class Booster:
-    def __init__(self, model_file=None, *, parse_only=False):
+    def __init__(self, model_file=None, *, parse_only=False, handle=None):
         self.handle = vp()
+        self.owned = handle is None
+        if handle is not None:
+            self.handle = handle
+            return
         check(lib().XGBoosterCreate(None, 0, C.byref(self.handle)))
         if model_file is not None:
             if parse_only:
@@ -333,10 +363,17 @@ class Booster:
         epi = Epilogue(int(exp10), float(scale))
         check(lib().qcoh_booster_predict_device(self.handle, dmat.handle, option_mask, ntree_limit, C.byref(epi), out.ptr))
 
+    @classmethod
+    def cached(cls, model_file):
+        """The process-wide cache's booster for this file (loaded on first request); owned by the cache."""
+        h = vp()
+        check(lib().qcoh_model_cache_get(os.fsencode(model_file), C.byref(h)))
+        return cls(handle=h)
+
     def free(self):
-        if self.handle:
+        if self.handle and self.owned:
             check(lib().XGBoosterFree(self.handle))
-            self.handle = vp()
+        self.handle = vp()
 
     def __del__(self):
         try:
@@ -429,7 +466,7 @@ class OhRun1:
         km, ncol = self.km, self.ncol
         o = Run1Out()
         res = {}
-        for name in ("OH", "OH_boost", "NDWET"):
+        for name in ("OH", "OH_boost", "NDWET", "LOSS_CH4", "LOSS_CO"):
             if device_out and name in device_out:
                 setattr(o, name, device_out[name].ptr)
             elif name in want or name == "OH":
@@ -451,6 +488,16 @@ class OhRun1:
                 res["pred"] = res["pred"][:n]
         res["diag"] = np.array(list(o.diag))
         return res
+
+    def set_booster(self, booster: Booster) -> None:
+        check(lib().qcoh_oh_set_booster(self.handle, booster.handle))
+        self.booster = booster
+
+    def select_model(self, pattern: str, nymd: int, nhms: int = 0) -> bool:
+        """Opt-in month roll-over: switch to the cached booster of the expanded file name."""
+        ch = C.c_int(0)
+        check(lib().qcoh_oh_select_model(self.handle, os.fsencode(pattern), nymd, nhms, C.byref(ch)))
+        return bool(ch.value)
 
     def get_diag(self, name: str) -> np.ndarray:
         """DIAG_<name> export of the last boost step (OH_StateSpecs.rc:41-73)."""

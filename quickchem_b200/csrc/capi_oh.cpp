@@ -59,7 +59,7 @@ struct Oh {
   // resident copies of host-provided inputs, one slot per input field
   static constexpr int kNumIn = 13 + 7 + 11 + 5 + 1 + 1;
   DevBuf<float> in[kNumIn];
-  DevBuf<float> PL_MOD, NDWET, sums[6], OH_ML, OH, OH_boost, X, pred, sza, lat_deg, so3;
+  DevBuf<float> PL_MOD, NDWET, sums[6], OH_ML, OH, OH_boost, X, pred, sza, lat_deg, so3, loss_ch4, loss_co;
   DevBuf<int> ctl;
   DevBuf<double> diag;
   PinBuf<float> h_sza, h_lat, h_lon;
@@ -111,6 +111,26 @@ int qcoh_oh_create(BoosterHandle booster, const qcoh_oh_config *cfg, qcoh_oh_han
   API_END
 }
 
+int qcoh_oh_set_booster(qcoh_oh_handle h, BoosterHandle booster) {
+  API_BEGIN
+  Oh *o = O(h);
+  Booster *b = B(booster);
+  if (!b->loaded) throw Error("Booster has no model: call XGBoosterLoadModel first");
+  if (b->host.num_feature != 27)
+    throw Error("OH_GridComp packs exactly 27 features (OH_GridCompMod.F90:228); the booster has " + std::to_string(b->host.num_feature));
+  ensure_device();
+  upload(b);
+  o->booster = b;
+  API_END
+}
+
+int qcoh_oh_get_booster(qcoh_oh_handle h, BoosterHandle *out) {
+  API_BEGIN
+  if (!out) throw Error("qcoh_oh_get_booster: out is NULL");
+  *out = O(h)->booster;
+  API_END
+}
+
 int qcoh_oh_get_diag(qcoh_oh_handle h, const char *name, float *out) {
   API_BEGIN
   Oh *o = O(h);
@@ -152,8 +172,7 @@ int qcoh_oh_run1(qcoh_oh_handle h, const qcoh_run1_in *in, qcoh_run1_out *out) {
   const qcoh_oh_config &c = o->cfg;
   const int nc = c.ncol, km = c.km;
   const size_t n2 = (size_t)nc, n3 = (size_t)nc * km, ne = (size_t)nc * (km + 1);
-  Run1Dev r;
-  memset(&r, 0, sizeof r);
+  Run1Dev r{};
   r.ncol = nc, r.km = km;
   r.eps = c.mapl_epsilon, r.avogad = c.mapl_avogad, r.runiv = c.mapl_runiv, r.r2d = c.mapl_radians_to_degrees;
   r.ohscale = c.ohscale, r.tropp_min = c.tropp_min, r.missing = c.missing;
@@ -213,6 +232,8 @@ int qcoh_oh_run1(qcoh_oh_handle h, const qcoh_run1_in *in, qcoh_run1_out *out) {
   if (want_diag) r.AREA = resident(o, Oh::kNumIn - 1, in->AREA, n2, "AREA");
   r.PL_MOD = o->PL_MOD.need(n3), r.NDWET = o->NDWET.need(n3);
   r.OH_ML = o->OH_ML.p, r.OH = o->OH.need(n3), r.OH_boost = o->OH_boost.need(n3);
+  r.LOSS_CH4 = out->LOSS_CH4 ? o->loss_ch4.need(n3) : nullptr;
+  r.LOSS_CO = out->LOSS_CO ? o->loss_co.need(n3) : nullptr;
   r.ctl = o->ctl.need(4);
   r.diag = o->diag.need(4);
   CU(cudaMemsetAsync(r.ctl, 0, 4 * sizeof(int), g.stream));
@@ -231,6 +252,8 @@ int qcoh_oh_run1(qcoh_oh_handle h, const qcoh_run1_in *in, qcoh_run1_out *out) {
     for (int i = 0; i < 6; ++i) r.sums[i] = o->sums[i].need(n3);
     r.lat_deg = o->lat_deg.need(n2), r.so3 = o->so3.need(n2);
     CU(launch_oh_sums(r, g.stream));
+    B(o->booster);  // a freed booster fails here rather than in a kernel
+    upload(o->booster);
     sync_const_top(o->booster);
     CU(cudaMemsetAsync(r.OH_ML, 0, n3 * 4, g.stream));  // self%OH_ML = 0.0 (:1559)
     if (npred && !out->X) {
@@ -282,6 +305,8 @@ int qcoh_oh_run1(qcoh_oh_handle h, const qcoh_run1_in *in, qcoh_run1_out *out) {
   deliver(out->OH, r.OH, n3);
   deliver(out->OH_boost, r.OH_boost, n3);
   deliver(out->NDWET, r.NDWET, n3);
+  deliver(out->LOSS_CH4, r.LOSS_CH4, n3);
+  deliver(out->LOSS_CO, r.LOSS_CO, n3);
   int inf_flags = 0;
   if (check_inf_after) CU(cudaMemcpyAsync(&inf_flags, r.ctl + 2, sizeof(int), cudaMemcpyDeviceToHost, g.stream));
   CU(cudaStreamSynchronize(g.stream));

@@ -274,6 +274,7 @@ int XGBoosterCreate(const DMatrixHandle dmats[], bst_ulong len, BoosterHandle *o
 int XGBoosterFree(BoosterHandle handle) {
   API_BEGIN
   Booster *b = B(handle);
+  if (b->cache_owned) throw Error("XGBoosterFree: this booster belongs to the model cache (qcoh_model_cache_clear frees it)");
   if (g_last_booster == b) g_last_booster = nullptr;
   if (g.ready) CU(cudaStreamSynchronize(g.stream));
   b->magic = 0;
@@ -285,6 +286,9 @@ int qcoh_booster_parse(BoosterHandle handle, const char *fname) {
   API_BEGIN
   Booster *b = B(handle);
   if (!fname) throw Error("model file name is NULL");
+  if (b->cache_owned) throw Error("this booster belongs to the model cache and cannot be reloaded");
+  // a reload replaces the device forest in place: nothing may still be reading it
+  if (b->uploaded && g.ready) CU(cudaStreamSynchronize(g.stream));
   HostForest hf = load_model_file(fname);
   FlatForest ff = flatten(hf);
   b->host = std::move(hf), b->flat = std::move(ff);
@@ -312,7 +316,7 @@ int XGBoosterSaveModel(BoosterHandle handle, const char *fname) {
 int XGDMatrixCreateFromMat(const float *data, bst_ulong nrow, bst_ulong ncol, float missing, DMatrixHandle *out) {
   API_BEGIN
   if (!out) throw Error("XGDMatrixCreateFromMat: out is NULL");
-  if (!data && nrow * ncol) throw Error("XGDMatrixCreateFromMat: data is NULL");
+  if (!data && nrow && ncol) throw Error("XGDMatrixCreateFromMat: data is NULL");
   ensure_device();
   std::unique_ptr<DMatrix> d(new DMatrix());
   d->nrow = nrow, d->ncol = ncol, d->missing = missing;

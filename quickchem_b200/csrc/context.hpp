@@ -176,6 +176,7 @@ struct Booster {
   uint32_t magic = kBoosterMagic;
   uint64_t version = 0;  // changes with every (re)load
   bool loaded = false, uploaded = false;
+  bool cache_owned = false;  // lives in the model cache (model_cache.cpp): not the caller's to free or reload
   HostForest host;
   FlatForest flat;
   std::vector<uint32_t> dev_nodes_host;  // the device form of the nodes (keys), kept for the constant-top table
@@ -185,6 +186,12 @@ struct Booster {
   DevBuf<int32_t> d_depth, d_orig;
   DevBuf<float> d_result;
   PinBuf<float> h_result;
+  Booster() = default;
+  Booster(const Booster &) = delete;
+  Booster &operator=(const Booster &) = delete;
+  ~Booster() {
+    if (dev.tex) cudaDestroyTextureObject(dev.tex);
+  }
 };
 
 struct DMatrix {

@@ -650,7 +650,8 @@ cudaError_t launch_oh_pack(const Run1Dev &r, int k1, float *X, cudaStream_t s) {
 }
 
 // oh_finalize (OH_GridCompMod.F90:1579-1599): OH_boost export, troposphere mask against the
-// climatological OH using the CURRENT model PL / TROPP, mol/mol -> molec/cm3.
+// climatological OH using the CURRENT model PL / TROPP, mol/mol -> molec/cm3; optionally the
+// loss frequencies k(T)[OH] the downstream CH4 / CO chemistry needs.
 __global__ void __launch_bounds__(256) oh_finalize_kernel(Run1Dev r, uint64_t n) {
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
   for (uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += stride) {
@@ -658,7 +659,11 @@ __global__ void __launch_bounds__(256) oh_finalize_kernel(Run1Dev r, uint64_t n)
     const float ml = r.OH_ML[e];
     if (r.OH_boost) r.OH_boost[e] = ml;
     const float oh = (r.PL_MOD[e] > r.TROPP[c]) ? ml : r.OH_CLIM[e];
-    r.OH[e] = __fmul_rn(__fmul_rn(oh, r.NDWET[e]), 1.0e-6f);
+    const float ohn = __fmul_rn(__fmul_rn(oh, r.NDWET[e]), 1.0e-6f);
+    r.OH[e] = ohn;
+    // first-order loss frequencies for the CH4 / CO consumers of OH (build-defined; qcoh.h): float64, rounded once
+    if (r.LOSS_CH4) r.LOSS_CH4[e] = (float)(2.45e-12 * exp(-1775.0 / (double)r.T_MOD[e]) * (double)ohn);
+    if (r.LOSS_CO) r.LOSS_CO[e] = (float)(1.5e-13 * (1.0 + 0.6 * ((double)r.PL_MOD[e] / 101325.0)) * (double)ohn);
   }
 }
 

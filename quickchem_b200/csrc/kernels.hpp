@@ -93,6 +93,7 @@ struct Run1Dev {
   float *lat_deg, *so3;              // [ncol] latarr, stratO3 (written by oh_sums)
   float *OH_ML;                      // persistent [km][ncol]
   float *OH, *OH_boost;              // [km][ncol]
+  float *LOSS_CH4, *LOSS_CO;         // optional [km][ncol] 1/s (build-defined)
   int *ctl;                          // [0] ksub (atomicMax) [1] tropp<=tropp_min count [2] matrix flags
   double *diag;                      // [4]
 };

@@ -19,6 +19,9 @@ namespace {
 // SAVE variables of the reference (OH_GridCompMod.F90:182,209): one booster per process
 BoosterHandle xx_bst = nullptr;
 bool first_time = true;
+// opt-in fix of SURVEY.md 0.5 (the file name carries the month but the booster is loaded once)
+bool reload_on_file_change = false;
+std::string loaded_fname;
 
 constexpr int64_t xx_param_count = 27;  // :228
 constexpr float xx_miss = -999.0f;      // :213
@@ -46,7 +49,10 @@ extern "C" void qcoh_predict_OH_reset(void) {
   if (xx_bst) XGBoosterFree(xx_bst);
   xx_bst = nullptr;
   first_time = true;
+  loaded_fname.clear();
 }
+
+extern "C" void qcoh_predict_OH_reload_on_file_change(int on) { reload_on_file_change = on != 0; }
 
 // Arrays are Fortran (icount, jcount, kcount) column-major == C [k][j][i]; the (i,j) members of bb
 // are [j][i].  Returns 0 (ESMF_SUCCESS) or -1 with XGBGetLastError() / the _ASSERT message.
@@ -70,6 +76,12 @@ extern "C" int qcoh_predict_OH_with_XGB(const char *xgb_fname, int icount, int j
     rc = XGDMatrixFree(xx_dmtrx);
     if (rc != 0) return -1;
     first_time = false;
+    loaded_fname = xgb_fname;
+  } else if (reload_on_file_change && loaded_fname != xgb_fname) {
+    // not in the reference: its SAVE'd booster keeps the first month's model for the whole run
+    rc = XGBoosterLoadModel(xx_bst, xgb_fname);
+    if (rc != 0) return -1;
+    loaded_fname = xgb_fname;
   }
 
   // ---- RUN: level slab (:275-301)

@@ -232,3 +232,103 @@ def test_native_nccl_allreduce_single_rank(capi):
     with pytest.raises(capi.QcohError, match="qcoh_comm_init first"):
         capi.comm_allreduce_sum([1.0])
 
+
+
+def test_loss_frequencies_for_ch4_co(capi, small_model_path):
+    """SURVEY.md 8(f)4 (build-defined, no reference counterpart): LOSS_CH4 = 2.45e-12 exp(-1775/T) [OH] and
+    LOSS_CO = 1.5e-13 (1 + 0.6 PL/101325) [OH] from the final OH (molec/cm3), float64 on the device and rounded
+    once — checked against numpy float64 on the returned OH, T and DIAG_PL (1e-6 relative, stated here)."""
+    fields = synth.raw_fields(6)
+    km, ncol = fields["T"].shape
+    oh = capi.OhRun1(capi.Booster(small_model_path), ncol, km, synth.MAPL)
+    got = oh.run(oh.make_in(fields), want=("OH", "LOSS_CH4", "LOSS_CO"))
+    pl = oh.get_diag("PL").astype(np.float64)
+    ohn, t = got["OH"].astype(np.float64), fields["T"].astype(np.float64)
+    assert _rel(got["LOSS_CH4"], 2.45e-12 * np.exp(-1775.0 / t) * ohn) <= 1e-6
+    assert _rel(got["LOSS_CO"], 1.5e-13 * (1.0 + 0.6 * pl / 101325.0) * ohn) <= 1e-6
+    assert np.all(got["LOSS_CH4"] > 0) and np.all(got["LOSS_CO"] > got["LOSS_CH4"])
+    # not requested => not produced, OH unchanged, also on a non-boost step
+    again = oh.run(oh.make_in(fields, need_to_call_boost=False), want=("OH", "LOSS_CO"))
+    assert "LOSS_CH4" not in again and np.array_equal(again["OH"], got["OH"])
+    assert np.array_equal(again["LOSS_CO"], got["LOSS_CO"])
+
+
+def _two_month_models(tmp_path):
+    from quickchem_b200 import xgbmodel
+
+    paths = {}
+    for mm, seed in ((7, 5), (8, 6)):
+        f = synth.prod_like_booster(n_trees=6, max_depth=6, n_sample=8000, grid_n=12, seed=seed)
+        paths[mm] = str(tmp_path / f"oh_M{mm:02d}.model")
+        xgbmodel.write_legacy_binary(f, paths[mm])
+    return str(tmp_path / "oh_M%m2.model"), paths
+
+
+def test_month_rollover_is_opt_in(capi, oracle, tmp_path):
+    """the reference expands `..._M%m2.model` every step but predicts with the booster it loaded
+    first.  qcoh_oh_run1 keeps that; qcoh_oh_select_model (template + cache + switch) is the opt-in fix."""
+    pattern, paths = _two_month_models(tmp_path)
+    fields = synth.raw_fields(6)
+    km, ncol = fields["T"].shape
+    ref = {mm: oracle.run1(oracle.Model(p), fields, synth.MAPL, nymd=20220801) for mm, p in paths.items()}
+    assert not np.array_equal(ref[7]["OH_boost"], ref[8]["OH_boost"])
+    capi.model_cache_clear()
+    july = capi.Booster.cached(capi.expand_template(pattern, 20220731))
+    oh = capi.OhRun1(july, ncol, km, synth.MAPL)
+    # default: 1 August still runs July's model (reference behaviour)
+    got = oh.run(oh.make_in(fields, nymd=20220801), want=("OH", "OH_boost"))
+    assert _rel(got["OH_boost"], ref[7]["OH_boost"]) <= REL_TOL_OH
+    assert oh.select_model(pattern, 20220731) is False
+    assert oh.select_model(pattern, 20220801) is True and capi.model_cache_size() == 2
+    got = oh.run(oh.make_in(fields, nymd=20220801), want=("OH", "OH_boost"))
+    assert _rel(got["OH_boost"], ref[8]["OH_boost"]) <= REL_TOL_OH
+    assert _rel(got["OH"], ref[8]["OH"]) <= REL_TOL_OH
+    # back and forth reuses the cached boosters (no reload), and the constant-memory tops follow the switch
+    assert oh.select_model(pattern, 20220715, 120000) is True and capi.model_cache_size() == 2
+    got = oh.run(oh.make_in(fields, nymd=20220801), want=("OH", "OH_boost"))
+    assert _rel(got["OH_boost"], ref[7]["OH_boost"]) <= REL_TOL_OH
+    with pytest.raises(capi.QcohError, match="No such file|cannot open|open"):
+        oh.select_model(pattern, 20220901)
+    oh.free()
+    capi.model_cache_clear()
+    assert capi.model_cache_size() == 0
+
+
+def test_booster_reload_in_place(capi, oracle, tmp_path):
+    """XGBoosterLoadModel on a booster that already holds a model replaces it (libxgboost semantics); the host
+    mirror uses exactly that when qcoh_predict_OH_reload_on_file_change(1) is set, and never otherwise."""
+    _, paths = _two_month_models(tmp_path)
+    rng = np.random.default_rng(3)
+    x = synth.quick_features(synth.raw_fields(6))[rng.integers(0, 6 * 36 * 72, 5000)]
+    b = capi.Booster(paths[7])
+    m = capi.DMatrix(x)
+    p7 = b.predict(m)
+    b.load_model(paths[8])
+    p8 = b.predict(m)
+    assert np.array_equal(p7, oracle.Model(paths[7]).predict(x)) and np.array_equal(p8, oracle.Model(paths[8]).predict(x))
+    assert not np.array_equal(p7, p8)
+    # the mirror
+    fields = synth.raw_fields(6)
+    km, ncol = fields["T"].shape
+    pl_mod = ((fields["PLE"][:-1] + fields["PLE"][1:]) * np.float32(0.5)).astype(np.float32)
+    X = synth.quick_features(fields)
+    bb = [np.ascontiguousarray(X[:ncol, f]) if f in (0, 21, 22, 26) else
+          (pl_mod if f == 1 else np.ascontiguousarray(X[:, f].reshape(km, ncol))) for f in range(27)]  # fmt: skip
+
+    def call(path):
+        out = np.zeros((km, ncol), np.float32)
+        assert capi.predict_OH_with_XGB(path, 6, ncol // 6, km, True, 4000.0, pl_mod, fields["TROPP"], bb, out) == 0
+        return out
+
+    L = capi.lib()
+    L.qcoh_predict_OH_reset()
+    try:
+        a7, a8_default = call(paths[7]), call(paths[8])
+        assert np.array_equal(a7, a8_default)  # SAVE'd booster: the second file name is ignored
+        L.qcoh_predict_OH_reload_on_file_change(1)
+        a8 = call(paths[8])
+        assert not np.array_equal(a7, a8)
+        assert np.array_equal(call(paths[7]), a7)
+    finally:
+        L.qcoh_predict_OH_reload_on_file_change(0)
+        L.qcoh_predict_OH_reset()

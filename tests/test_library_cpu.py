@@ -222,3 +222,41 @@ def test_product_does_not_touch_the_oracle():
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), fn
     out = os.popen(f"ldd {os.path.join(pkg, 'libqcoh.so')}").read()
     assert "oracle" not in out
+
+
+def test_expand_template_like_fill_grads_template(capi):
+    """XGBoostFile carries %m2 (OH_instance_OH.rc:20) and is expanded on every Run1 (OH_GridCompMod.F90:1187)."""
+    e = capi.expand_template
+    prod = "/discover/x/xgboh_UpDwnALBUVSZAAll_NoGMIALB_NoScale_NoRegressor_NewXGB_M%m2.model"
+    assert e(prod, 20220726) == prod.replace("%m2", "07")
+    assert e(prod, 20221201, 0) == prod.replace("%m2", "12")
+    assert e("%y4-%y2-%m1-%m2-%mc-%Mc-%MC-%d1-%d2-%h1-%h2-%n2-%j3-100%%", 20240305, 93000) == \
+        "2024-24-3-03-mar-Mar-MAR-5-05-9-09-30-065-100%"  # fmt: skip
+    assert e("%j3", 20230305) == "064" and e("%j3", 20241231) == "366"
+    assert e("no tokens", 20220101) == "no tokens" and e("", 20220101) == ""
+    for bad, nymd in (("%q9", 20220726), ("abc%", 20220726), ("%m", 20220726), ("%m2", 20221326), ("%m2", -5)):
+        with pytest.raises(capi.QcohError, match="qcoh_expand_template"):
+            e(bad, nymd)
+    buf = ctypes.create_string_buffer(4)
+    assert capi.lib().qcoh_expand_template(b"%y4", 20220101, 0, buf, 4) == -1  # needs 5 bytes with the NUL
+    assert capi.lib().qcoh_expand_template(b"%y2x", 20220101, 0, buf, 4) == 0 and buf.value == b"22x"
+
+
+def test_model_cache_without_gpu(capi):
+    """The cache parses on first request and hands out the same handle afterwards; its boosters are not the
+    caller's to free or reload.  (Upload happens at first use on the GPU — not exercised here.)"""
+    capi.model_cache_clear()
+    p = os.path.join(ROOT, "tests", "golden", "tiny.model")
+    a, b = capi.Booster.cached(p), capi.Booster.cached(p)
+    assert a.handle.value == b.handle.value and capi.model_cache_size() == 1
+    c = capi.Booster.cached(os.path.join(ROOT, "tests", "golden", "tiny.json"))
+    assert c.handle.value != a.handle.value and capi.model_cache_size() == 2
+    assert a.info().num_trees == c.info().num_trees
+    L = capi.lib()
+    assert L.XGBoosterFree(a.handle) == -1 and "model cache" in capi.last_error()
+    assert L.XGBoosterLoadModel(a.handle, os.fsencode(p)) == -1 and "model cache" in capi.last_error()
+    with pytest.raises(capi.QcohError, match="No such file"):
+        capi.Booster.cached("/nonexistent/oh_M07.model")
+    assert capi.model_cache_size() == 2
+    capi.model_cache_clear()
+    assert capi.model_cache_size() == 0
