@@ -127,6 +127,13 @@ int qcoh_booster_get_info(BoosterHandle handle, qcoh_booster_info *out);
 int qcoh_booster_get_flat(BoosterHandle handle, const uint32_t **nodes_xy, const uint32_t **tree_offset,
                           const int32_t **tree_depth, const int32_t **orig_id);
 
+/* Two-level records (DESIGN.md "Two levels per gather"), for inspection/tests: 16-byte records
+ * {w0, w1, w2, w3}; tree_slot[num_trees] = first record of each tree; top_xy[num_trees][16][2] = the complete
+ * heap-ordered levels 0..3 that go to constant memory.  Fails (-1, reason in XGBGetLastError) when the
+ * booster does not qualify (> 2^17 record blocks in a tree). */
+int qcoh_booster_get_duo(BoosterHandle handle, const uint32_t **rec, const uint32_t **tree_slot, const uint32_t **top_xy,
+                         int64_t *num_slots);
+
 /* ---- device-resident predict -------------------------------------------------------- */
 /* A DMatrix whose storage is allocated in HBM and filled by the caller (device pointer
  * returned by qcoh_dmatrix_device_ptr) or by qcoh_dmatrix_upload.  Call qcoh_dmatrix_seal

@@ -67,7 +67,7 @@ XGB_SYMBOLS = ("XGBoosterLoadModel", "XGBoosterSaveModel", "XGDMatrixSaveBinary"
 QCOH_SYMBOLS = ("qcoh_version", "qcoh_device_count", "qcoh_set_device", "qcoh_host_alloc", "qcoh_host_free",
                 "qcoh_device_alloc", "qcoh_device_free", "qcoh_memcpy_h2d", "qcoh_memcpy_d2h",
                 "qcoh_device_synchronize", "qcoh_timer_start", "qcoh_timer_stop", "qcoh_flush_l2",
-                "qcoh_booster_parse", "qcoh_booster_get_info", "qcoh_booster_get_flat",
+                "qcoh_booster_parse", "qcoh_booster_get_info", "qcoh_booster_get_flat", "qcoh_booster_get_duo",
                 "qcoh_dmatrix_create_device", "qcoh_dmatrix_device_ptr", "qcoh_dmatrix_upload", "qcoh_dmatrix_seal",
                 "qcoh_booster_predict_device", "qcoh_set_param", "qcoh_launch_count", "qcoh_oh_create",
                 "qcoh_oh_run1", "qcoh_oh_free", "qcoh_oh_get_diag", "qcoh_predict_OH_with_XGB", "qcoh_predict_OH_reset",
@@ -113,6 +113,8 @@ def lib():
         L.qcoh_booster_get_info.argtypes = [vp, C.POINTER(BoosterInfo)]
         L.qcoh_booster_get_flat.argtypes = [vp, C.POINTER(C.POINTER(C.c_uint32)), C.POINTER(C.POINTER(C.c_uint32)),
                                             C.POINTER(C.POINTER(C.c_int32)), C.POINTER(C.POINTER(C.c_int32))]  # fmt: skip
+        L.qcoh_booster_get_duo.argtypes = [vp, C.POINTER(C.POINTER(C.c_uint32)), C.POINTER(C.POINTER(C.c_uint32)),
+                                           C.POINTER(C.POINTER(C.c_uint32)), C.POINTER(C.c_int64)]  # fmt: skip
         L.qcoh_dmatrix_create_device.argtypes = [u64, u64, C.c_float, C.POINTER(vp)]
         L.qcoh_dmatrix_device_ptr.argtypes = [vp, C.POINTER(vp)]
         L.qcoh_dmatrix_upload.argtypes = [vp, vp, u64, u64]
@@ -341,6 +343,15 @@ class Booster:
         depth = np.ctypeslib.as_array(pd, (t,)).copy() if t else np.zeros(0, np.int32)
         orig = np.ctypeslib.as_array(pi, (n,)).copy() if n else np.zeros(0, np.int32)
         return nodes, off, depth, orig
+
+    def duo(self):
+        """(records[nslots,4] uint32, tree_slot[T], top_xy[T,16,2]) copies of the two-level record layout; raises
+        if the booster does not qualify."""
+        pr, ps, pt, n = C.POINTER(C.c_uint32)(), C.POINTER(C.c_uint32)(), C.POINTER(C.c_uint32)(), C.c_int64()
+        check(lib().qcoh_booster_get_duo(self.handle, C.byref(pr), C.byref(ps), C.byref(pt), C.byref(n)))
+        nt = self.info().num_trees
+        rec = np.ctypeslib.as_array(pr, (n.value * 4,)).reshape(n.value, 4).copy()
+        return rec, np.ctypeslib.as_array(ps, (nt,)).copy(), np.ctypeslib.as_array(pt, (nt * 32,)).reshape(nt, 16, 2).copy()
 
     def predict(self, dmat: DMatrix, option_mask=0, ntree_limit=0, training=0) -> np.ndarray:
         """XGBoosterPredict_f(handle, dmat, option_mask, ntree_limit, training, length, prediction).

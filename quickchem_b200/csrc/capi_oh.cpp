@@ -254,7 +254,7 @@ int qcoh_oh_run1(qcoh_oh_handle h, const qcoh_run1_in *in, qcoh_run1_out *out) {
     CU(launch_oh_sums(r, g.stream));
     B(o->booster);  // a freed booster fails here rather than in a kernel
     upload(o->booster);
-    sync_const_top(o->booster);
+    sync_const_top(o->booster, true);  // clean tiles walk the two-level records when the booster qualifies
     CU(cudaMemsetAsync(r.OH_ML, 0, n3 * 4, g.stream));  // self%OH_ML = 0.0 (:1559)
     if (npred && !out->X) {
       // fused: pack (:303-345) + create (:347) + predict (:356) + 10**x (:369) * OHscale (:1569) in one

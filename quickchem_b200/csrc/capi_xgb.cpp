@@ -21,11 +21,7 @@ void upload(Booster *b) {
       float thr;
       memcpy(&thr, &dev_nodes[2 * i], 4);
       if (std::isnan(thr)) throw Error("split threshold is NaN (node " + std::to_string(i) + ")");
-      thr += 0.0f;  // -0.0 -> +0.0
-      uint32_t bits;
-      memcpy(&bits, &thr, 4);
-      const uint32_t key = bits ^ ((bits >> 31) ? 0xFFFFFFFFu : 0x80000000u);
-      dev_nodes[2 * i] = 0u - key;  // key >= 0x007FFFFF (-inf), never 0
+      dev_nodes[2 * i] = neg_threshold_key(thr);  // key >= 0x007FFFFF (-inf), never 0
     }
     CU(cudaMemcpy(b->d_nodes.need(nn), dev_nodes.data(), nn * 8, cudaMemcpyHostToDevice));
     b->dev_nodes_host = std::move(dev_nodes);
@@ -62,17 +58,60 @@ void upload(Booster *b) {
     td.readMode = cudaReadModeElementType;
     CU(cudaCreateTextureObject(&b->dev.tex, &rd, &td, nullptr));
   }
+  // two-level records, when every tree qualifies
+  if (b->dev.tex4) cudaDestroyTextureObject(b->dev.tex4);
+  b->dev.tex4 = 0, b->dev.recs = nullptr, b->dev.duo_ready = 0;
+  if (b->duo.ok && b->duo.num_slots() > 0 && b->duo.num_slots() < ((int64_t)1 << 27)) {
+    const size_t ns = (size_t)b->duo.num_slots();
+    CU(cudaMemcpy(b->d_recs.need(ns), b->duo.rec.data(), ns * 16, cudaMemcpyHostToDevice));
+    cudaResourceDesc rd;
+    memset(&rd, 0, sizeof rd);
+    rd.resType = cudaResourceTypeLinear;
+    rd.res.linear.devPtr = b->d_recs.p;
+    rd.res.linear.desc = cudaCreateChannelDesc<uint4>();
+    rd.res.linear.sizeInBytes = ns * 16;
+    cudaTextureDesc td;
+    memset(&td, 0, sizeof td);
+    td.readMode = cudaReadModeElementType;
+    CU(cudaCreateTextureObject(&b->dev.tex4, &rd, &td, nullptr));
+    b->dev.recs = b->d_recs.p;
+  }
   b->uploaded = true;
 }
 
-// the constant-memory table of tree tops belongs to one booster at a time
+// The constant-memory table of tree tops belongs to one booster at a time, in one of two layouts: the first
+// levels of the depth-ordered nodes (walk_group), or the complete heap-ordered tops of the two-level records
+// (walk_group_duo).  allow_duo: the caller's next launches are clean-matrix sums, which the two-level kernel
+// serves when the booster qualifies; anything else then runs without a constant table (still correct).
 static uint64_t g_const_top_owner = 0;
-static int g_const_top_levels = 0;
-void sync_const_top(Booster *b) {
+static int g_const_top_levels = 0;  // kConstDuo = two-level layout
+constexpr int kConstDuo = -1;
+bool duo_wanted(const Booster *b) {
+  if (b->dev.recs == nullptr || b->dev.tex == 0 || g.tun.duo == 0) return false;
+  if (g.tun.duo > 0) return true;
+  // default: on, unless an experiment knob of the 8-byte-node kernel is set
+  return kDuoDefault && g.tun.variant == 0 && g.tun.park != 0 && g.tun.top_levels < 0 && g.tun.ilp == 0 && g.tun.minb == 0;
+}
+void sync_const_top(Booster *b, bool allow_duo) {
+  b->dev.const_top_levels = 0, b->dev.duo_ready = 0;
+  if (allow_duo && duo_wanted(b)) {
+    if (g_const_top_owner != b->version || g_const_top_levels != kConstDuo) {
+      if (upload_const_duo(b->duo.top_xy.data(), b->duo.tree_slot.data(), b->dev.ntree, g.stream) == cudaSuccess) {
+        g_const_top_owner = b->version, g_const_top_levels = kConstDuo;
+      } else {
+        (void)cudaGetLastError();
+        g_const_top_owner = 0;
+      }
+    }
+    if (g_const_top_owner == b->version && g_const_top_levels == kConstDuo) {
+      b->dev.duo_ready = 1;
+      return;
+    }
+  }
   const int want = g.tun.top_levels < 0 ? 4 : g.tun.top_levels;
-  b->dev.const_top_levels = 0;
   if (want <= 0) return;
   if (g_const_top_owner != b->version || g_const_top_levels != want) {
+    g_const_top_owner = 0;
     if (upload_const_top(b->dev_nodes_host.data(), b->flat.tree_offset.data(), b->dev.ntree, want, g.stream) != cudaSuccess) {
       (void)cudaGetLastError();
       return;  // does not fit: the kernel runs without the table
@@ -106,11 +145,11 @@ static void predict_into(Booster *b, DMatrix *d, int option_mask, unsigned ntree
   if (d->ncol > b->host.num_feature)
     throw Error("Check failed: Number of columns does not match number of features in booster. Columns: " +
                 std::to_string(d->ncol) + " Features: " + std::to_string(b->host.num_feature));
-  sync_const_top(b);
   PredictArgs a;
   a.X = d->X.p, a.nrow = d->nrow, a.ncol = (int32_t)d->ncol, a.missing = d->missing;
   a.has_missing = ((d->hflags & 1) || d->ncol < b->host.num_feature) ? 1 : 0;
   a.pred_leaf = (option_mask & 2) ? 1 : 0;
+  sync_const_top(b, !a.has_missing && !a.pred_leaf);
   a.ntree_used = (int32_t)trees_used(b, ntree_limit);
   a.exp10 = epi ? epi->exp10 : 0;
   a.scale = epi ? epi->scale : 1.f;
@@ -189,7 +228,7 @@ static void create_pipelined(DMatrix *d, const float *data, Booster *b) {
   float *sdev = nullptr, *shost = nullptr;
   if (spec) {
     upload(b);
-    sync_const_top(b);
+    sync_const_top(b, ncol >= b->host.num_feature);  // chunks with missing entries then walk without the table
     if (g_spare_spec.cap >= nrow && g_spare_spec.p) d->spec_dev.swap(g_spare_spec);
     sdev = d->spec_dev.need(nrow);
     if (g_spare_pin.cap >= nrow && g_spare_pin.p) d->spec_host.swap(g_spare_pin);
@@ -291,7 +330,8 @@ int qcoh_booster_parse(BoosterHandle handle, const char *fname) {
   if (b->uploaded && g.ready) CU(cudaStreamSynchronize(g.stream));
   HostForest hf = load_model_file(fname);
   FlatForest ff = flatten(hf);
-  b->host = std::move(hf), b->flat = std::move(ff);
+  DuoForest df = build_duo(ff, hf.num_feature);
+  b->host = std::move(hf), b->flat = std::move(ff), b->duo = std::move(df);
   b->loaded = true, b->uploaded = false;
   b->version = ++g_version_counter;
   API_END
@@ -628,6 +668,8 @@ int qcoh_set_param(const char *name, const char *value) {
   else if (n == "top_levels") g.tun.top_levels = v;
   else if (n == "park") g.tun.park = v;
   else if (n == "minb") g.tun.minb = v;
+  else if (n == "duo") g.tun.duo = v;
+  else if (n == "duo_mask") g.tun.duo_mask = v;
   else if (n == "speculate") g.speculate = v;
   else if (n == "chunk_rows") g.chunk_rows = v > 0 ? ((uint64_t)v + 255) / 256 * 256 : (1ull << 21);
   else throw Error("qcoh_set_param: unknown parameter '" + n + "'");
@@ -659,6 +701,19 @@ int qcoh_booster_get_flat(BoosterHandle handle, const uint32_t **nodes_xy, const
   if (tree_offset) *tree_offset = b->flat.tree_offset.data();
   if (tree_depth) *tree_depth = b->flat.tree_depth.data();
   if (orig_id) *orig_id = b->flat.orig_id.data();
+  API_END
+}
+
+int qcoh_booster_get_duo(BoosterHandle handle, const uint32_t **rec, const uint32_t **tree_slot, const uint32_t **top_xy,
+                         int64_t *num_slots) {
+  API_BEGIN
+  Booster *b = B(handle);
+  if (!b->loaded) throw Error("Booster has no model");
+  if (!b->duo.ok) throw Error("two-level records are not available for this booster: " + b->duo.why);
+  if (rec) *rec = b->duo.rec.data();
+  if (tree_slot) *tree_slot = b->duo.tree_slot.data();
+  if (top_xy) *top_xy = b->duo.top_xy.data();
+  if (num_slots) *num_slots = b->duo.num_slots();
   API_END
 }
 

@@ -181,6 +181,8 @@ struct Booster {
   FlatForest flat;
   std::vector<uint32_t> dev_nodes_host;  // the device form of the nodes (keys), kept for the constant-top table
   DeviceForest dev;
+  DuoForest duo;            // two-level records (forest.hpp); built with the model, ok == false if it does not qualify
+  DevBuf<uint4> d_recs;
   DevBuf<uint2> d_nodes;
   DevBuf<uint32_t> d_off;
   DevBuf<int32_t> d_depth, d_orig;
@@ -191,6 +193,7 @@ struct Booster {
   Booster &operator=(const Booster &) = delete;
   ~Booster() {
     if (dev.tex) cudaDestroyTextureObject(dev.tex);
+    if (dev.tex4) cudaDestroyTextureObject(dev.tex4);
   }
 };
 
@@ -234,6 +237,7 @@ inline DMatrix *D(DMatrixHandle h) {
 
 // capi_xgb.cpp
 void upload(Booster *b);
-void sync_const_top(Booster *b);  // make the constant-memory table of tree tops hold this booster
+// make the constant-memory table of tree tops hold this booster (see capi_xgb.cpp)
+void sync_const_top(Booster *b, bool allow_duo);
 
 }  // namespace qcoh

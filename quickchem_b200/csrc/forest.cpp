@@ -781,4 +781,81 @@ FlatForest flatten(const HostForest &f) {
   return out;
 }
 
+// ---- two-level records --------------------------------------------------------------------------
+DuoForest build_duo(const FlatForest &f, uint32_t num_feature) {
+  DuoForest out;
+  const size_t ntree = f.tree_depth.size();
+  auto X = [&](uint32_t n) { return f.nodes_xy[2 * (size_t)n]; };
+  auto REL = [&](uint32_t n) { return f.nodes_xy[2 * (size_t)n + 1] & kMetaRelMask; };
+  auto FEAT = [&](uint32_t n) { return f.nodes_xy[2 * (size_t)n + 1] >> kMetaFeatShift; };
+  auto thr_word = [&](uint32_t n) -> uint32_t {
+    if (REL(n) == 0) return 0u;  // leaf child: compared against key 0 of the sentinel slot, never carries
+    float thr;
+    const uint32_t b = X(n);
+    memcpy(&thr, &b, 4);
+    return neg_threshold_key(thr);
+  };
+  constexpr uint32_t kRow = 1u << kDuoTop;  // heap entries per tree (entry 0 unused), and level-kDuoTop roots
+  for (size_t t = 0; t < ntree; ++t) {
+    const uint32_t n0 = f.tree_offset[t];
+    // complete heap-ordered top: node[i] = the real node at heap position i, or the leaf it pads
+    uint32_t node[2 * kRow];
+    bool pad[2 * kRow];
+    node[1] = n0, pad[1] = false;
+    out.top_xy.resize(out.top_xy.size() + 2 * kRow, 0u);
+    uint32_t *top = out.top_xy.data() + out.top_xy.size() - 2 * kRow;
+    for (uint32_t i = 1; i < kRow; ++i) {
+      const uint32_t n = node[i];
+      if (!pad[i] && REL(n) != 0) {
+        top[2 * i] = thr_word(n), top[2 * i + 1] = FEAT(n) << kMetaFeatShift;
+        node[2 * i] = n + REL(n), node[2 * i + 1] = n + REL(n) + 1;
+        pad[2 * i] = pad[2 * i + 1] = false;
+      } else {  // a leaf above level kDuoTop, or padding below one: never right
+        top[2 * i] = 0u, top[2 * i + 1] = num_feature << kMetaFeatShift;
+        node[2 * i] = node[2 * i + 1] = n;
+        pad[2 * i] = pad[2 * i + 1] = true;
+      }
+    }
+    // tree bases on 128-byte lines
+    while ((out.rec.size() / 4) % 8) out.rec.insert(out.rec.end(), 4, 0u);
+    const size_t base = out.rec.size() / 4;
+    out.tree_slot.push_back((uint32_t)base);
+    std::vector<uint32_t> root_of;  // tree-local slot -> root node (global index), ~0u = unused slot
+    for (uint32_t i = kRow; i < 2 * kRow; ++i) root_of.push_back(node[i]);  // padded leaves become terminal records
+    for (size_t s = 0; s < root_of.size(); ++s) {
+      const uint32_t n = root_of[s];
+      uint32_t w[4] = {0u, 0u, 0u, 0u};
+      if (n != ~0u) {
+        if (REL(n) == 0) {
+          w[0] = X(n), w[1] = (uint32_t)f.orig_id[n];  // terminal: value bits, XGBoost node id
+        } else {
+          const uint32_t kids[2] = {n + REL(n), n + REL(n) + 1};
+          const size_t blk = root_of.size() / 4;
+          if (blk >= (1u << (32 - kDuoBlkShift))) {
+            out.why = "tree " + std::to_string(t) + " needs more than 2^17 record blocks";
+            return out;
+          }
+          for (int c = 0; c < 2; ++c) {
+            if (REL(kids[c]) == 0) {
+              root_of.push_back(kids[c]), root_of.push_back(~0u);
+            } else {
+              root_of.push_back(kids[c] + REL(kids[c])), root_of.push_back(kids[c] + REL(kids[c]) + 1);
+            }
+          }
+          w[0] = thr_word(n), w[1] = thr_word(kids[0]), w[2] = thr_word(kids[1]);
+          const uint32_t fl = REL(kids[0]) ? FEAT(kids[0]) : num_feature, fr = REL(kids[1]) ? FEAT(kids[1]) : num_feature;
+          w[3] = ((uint32_t)blk << kDuoBlkShift) | (fl << 10) | (fr << 5) | FEAT(n);
+        }
+      }
+      out.rec.insert(out.rec.end(), w, w + 4);
+    }
+    if (out.rec.size() / 4 > 0x7FFFFFFFull) {
+      out.why = "forest needs more than 2^31 records";
+      return out;
+    }
+  }
+  out.ok = true;
+  return out;
+}
+
 }  // namespace qcoh

@@ -6,6 +6,7 @@
 // Pure C++ (no CUDA), so it is testable on a box without a GPU.
 #pragma once
 #include <cstdint>
+#include <cstring>
 #include <string>
 #include <vector>
 
@@ -56,6 +57,36 @@ struct FlatForest {
   int32_t max_depth = 0;
   int64_t num_nodes() const { return (int64_t)orig_id.size(); }
 };
+
+// Device form of a split threshold: -key(thr) mod 2^32, key = order-preserving integer image of the
+// float with -0.0 folded into +0.0 (kernels.cu "Order-preserving integer keys").  Never 0.
+inline uint32_t neg_threshold_key(float thr) {
+  thr += 0.0f;
+  uint32_t bits;
+  memcpy(&bits, &thr, 4);
+  return 0u - (bits ^ ((bits >> 31) ? 0xFFFFFFFFu : 0x80000000u));
+}
+
+// Two-level records (DESIGN.md "Two levels per gather").  Levels 0..kDuoTop-1 of every tree are a COMPLETE
+// heap-ordered top (entry i = 1..15, children 2i and 2i+1; `top_xy` row of 16 {x, feat << 26} pairs per
+// tree, entry 0 unused) served from constant memory; a leaf above level kDuoTop is padded downwards with
+// never-right dummy nodes (x = 0, feat = num_feature).  Below, one 16-byte record holds a node at even depth
+// AND its two children, so one gather decides two levels.  {w0, w1, w2} = -key(threshold) of root / left / right (0 where that child is a leaf),
+// w3 = blk << 15 | feat(left) << 10 | feat(right) << 5 | feat(root); the four grandchild records sit
+// contiguously at tree-local slots blk*4 + 2*right1 + right2.  A leaf is a terminal record (w3 == 0,
+// w0 = value bits, w1 = XGBoost node id); a leaf CHILD has feature num_feature (whose key is 0: never
+// "right") and its terminal record sits at slot blk*4 + 2*side.
+constexpr int kDuoTop = 4;
+constexpr uint32_t kDuoBlkShift = 15;
+struct DuoForest {
+  bool ok = false;                    // false: some tree does not qualify (reason in `why`)
+  std::string why;
+  std::vector<uint32_t> rec;          // 4 words per slot
+  std::vector<uint32_t> tree_slot;    // [ntree] global slot of the tree's 16 level-kDuoTop records
+  std::vector<uint32_t> top_xy;       // [ntree][16][2] heap-ordered tops for the constant-memory table
+  int64_t num_slots() const { return (int64_t)(rec.size() / 4); }
+};
+DuoForest build_duo(const struct FlatForest &f, uint32_t num_feature);
 
 // Throws std::runtime_error with libxgboost-style messages on malformed / unsupported input.
 HostForest load_model_file(const std::string &path);

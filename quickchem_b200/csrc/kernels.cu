@@ -102,8 +102,12 @@ __device__ __forceinline__ uint32_t step_index(uint32_t idx, uint32_t rel, uint3
 // a tree in breadth-first order are exactly its levels 0..CTOP-1.  Constant loads go through the
 // constant cache, not the LSU / TEX data pipes; lanes of a warp mostly agree at those levels, so the
 // per-address serialisation of divergent constant loads stays short.
-constexpr int kConstTopNodes = 8000;  // 64 000 B of the 64 KB constant bank
+constexpr int kConstTopNodes = 7680;  // 61 440 B of the 64 KB constant bank (480 trees at 4 levels)
 __constant__ uint2 c_top[kConstTopNodes];
+// two-level records: in that mode c_top holds DuoForest::top_xy (complete heap-ordered tops) instead, and
+// c_duo_base the global index of each tree's first record (the block pointers are tree-relative)
+constexpr int kConstDuoTrees = kConstTopNodes >> kDuoTop;
+__constant__ uint32_t c_duo_base[kConstDuoTrees];
 
 cudaError_t upload_const_top(const uint32_t *dev_nodes_xy, const uint32_t *tree_offset, int ntree, int levels, cudaStream_t s) {
   const int stride = 1 << levels;
@@ -117,6 +121,13 @@ cudaError_t upload_const_top(const uint32_t *dev_nodes_xy, const uint32_t *tree_
     }
   }
   return cudaMemcpyToSymbolAsync(c_top, host, sizeof(uint2) * (size_t)ntree * stride, 0, cudaMemcpyHostToDevice, s);
+}
+
+cudaError_t upload_const_duo(const uint32_t *top_xy, const uint32_t *tree_slot, int ntree, cudaStream_t s) {
+  if (ntree > kConstDuoTrees) return cudaErrorInvalidValue;
+  cudaError_t e = cudaMemcpyToSymbolAsync(c_top, top_xy, sizeof(uint2) * ((size_t)ntree << kDuoTop), 0, cudaMemcpyHostToDevice, s);
+  if (e != cudaSuccess) return e;
+  return cudaMemcpyToSymbolAsync(c_duo_base, tree_slot, sizeof(uint32_t) * (size_t)ntree, 0, cudaMemcpyHostToDevice, s);
 }
 
 // TEXMODE is a bit mask over the ILP trees in flight: tree j fetches its nodes through the texture pipe
@@ -204,6 +215,95 @@ __device__ __forceinline__ void walk_group(const uint2 *__restrict__ nodes, cuda
   for (int j = 0; j < ILP; ++j) xbits[j] = nd[j].x;
 }
 
+// ---- two levels per gather (forest.hpp DuoForest) -----------------------------------------------------
+// Levels 0..3 come from constant memory as above (every tree of a qualifying booster has no leaf there, so
+// the prologue is branch-free); from level 4 on one 16-byte record {root, left, right thresholds; features;
+// block pointer} decides two levels, and the four possible successors are contiguous.  Against the 8-byte
+// nodes this halves the dependent gathers of a walk and takes ~40 % of the distinct lines per warp request
+// off the L1TEX data pipes (tools/replay_two_level_records.py).  Clean matrix (no missing entry) only.
+__device__ __forceinline__ uint32_t add_carry_out(uint32_t a, uint32_t b) {
+  uint32_t c;
+  asm("{\n\t.reg .u32 t;\n\tadd.cc.u32 t, %1, %2;\n\taddc.u32 %0, 0, 0;\n\t}" : "=r"(c) : "r"(a), "r"(b));
+  return c;
+}
+// Default shape (B200, profiles/README.md "two-level records"): 6 trees in flight, 4 of them gathering through
+// the texture pipe, 5 resident CTAs per SM (45 registers) — LSU and TEX data pipes, ALU and issue slots all end
+// up at 76-84 % busy.
+constexpr int kDuoIlp = 6, kDuoTexMask = 0x36, kDuoMinBlocks = 5;
+template <int ILP, int TEXMODE>
+__device__ __forceinline__ void walk_group_duo(const uint4 *__restrict__ recs, cudaTextureObject_t tex4,
+                                               const int32_t *__restrict__ tdepth, int t, uint32_t my_saddr, uint32_t (&xbits)[ILP]) {
+  constexpr int CTOP = kDuoTop;
+  int depth = CTOP - 1;  // at least one record (a shallower tree ends in the terminal records of its padded leaves)
+  uint32_t idx[ILP];
+#pragma unroll
+  for (int j = 0; j < ILP; ++j) {
+    depth = max(depth, __ldg(tdepth + t + j) & 0xFF);
+    idx[j] = 1u;  // heap position in the complete top: children of i are 2i and 2i + 1
+  }
+#pragma unroll
+  for (int d = 0; d < CTOP; ++d) {
+#pragma unroll
+    for (int j = 0; j < ILP; ++j) {
+      const uint2 nd = c_top[((uint32_t)(t + j) << CTOP) + idx[j]];
+      const uint32_t sa = my_saddr + __byte_perm(nd.y, 0u, 0x4434);
+      uint32_t kv;
+      asm volatile("ld.shared.u32 %0, [%1];" : "=r"(kv) : "r"(sa));
+      idx[j] = step_index(idx[j], idx[j], nd.x, kv);  // 2i + right
+    }
+  }
+  uint4 r[ILP];
+  uint32_t walking[ILP];
+#pragma unroll
+  for (int j = 0; j < ILP; ++j) {
+    idx[j] += c_duo_base[t + j] - (1u << CTOP);  // heap position 16..31 -> record index
+    r[j] = make_uint4(0u, 0u, 0u, 0u);
+    walking[j] = 1u;
+  }
+  // the terminal record of a leaf at depth D is rooted at depth D (D even) or D + 1 (D odd).  Only the
+  // gather is predicated (a lane that has reached its terminal record stops fetching and keeps it); the
+  // arithmetic below runs unconditionally, phase by phase across the ILP trees, so that the trees'
+  // dependent chains interleave: on a terminal record (w3 == 0) it reads feature 0 and leaves walking at 0.
+  for (int d = CTOP; d <= depth + 1; d += 2) {
+#pragma unroll
+    for (int j = 0; j < ILP; ++j) {
+      if (walking[j] != 0u) {
+        if ((TEXMODE >> j) & 1)
+          r[j] = tex1Dfetch<uint4>(tex4, (int)idx[j]);
+        else
+          r[j] = __ldg(recs + idx[j]);
+      }
+    }
+    uint32_t kv[ILP], right1[ILP];
+#pragma unroll
+    for (int j = 0; j < ILP; ++j) {
+      // srow[feat(root)][tid]: feat is the low 5 bits of w3; one AND + one multiply-add
+      uint32_t sa;
+      asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(sa) : "r"(r[j].w & 31u), "r"((uint32_t)(kStride * 4)), "r"(my_saddr));
+      asm volatile("ld.shared.u32 %0, [%1];" : "=r"(kv[j]) : "r"(sa));
+    }
+#pragma unroll
+    for (int j = 0; j < ILP; ++j) {
+      right1[j] = add_carry_out(r[j].x, kv[j]);
+      // feat(left) sits at bits 14..10 — already feat * 1024 —, feat(right) at 9..5
+      const uint32_t ms = right1[j] ? (r[j].w << 5) : r[j].w;
+      asm volatile("ld.shared.u32 %0, [%1];" : "=r"(kv[j]) : "r"(my_saddr + (ms & (31u << 10))));
+    }
+#pragma unroll
+    for (int j = 0; j < ILP; ++j) {
+      const uint32_t xs = right1[j] ? r[j].z : r[j].y;
+      const uint32_t blk = r[j].w >> kDuoBlkShift;
+      // next record = base + blk * 4 + 2 * right1 + right2
+      const uint32_t half = blk + blk + right1[j];
+      idx[j] = step_index(c_duo_base[t + j] + half, half, xs, kv[j]);
+      walking[j] = blk;  // 0: this was a terminal record, r[j].x is the leaf value
+      asm volatile("" : "+r"(walking[j]));
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < ILP; ++j) xbits[j] = r[j].x;
+}
+
 __device__ __forceinline__ float export_transform(float acc, int exp10_on, float scale) {
   if (!exp10_on) return acc;
   // OH_ML = 10.0 ** pred (OH_GridCompMod.F90:369), then OH_ML * OHscale (:1569): two float32
@@ -239,60 +339,66 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       : "memory");
 }
 
+// Stage the CTA's rows (one contiguous run of X) into the transposed key tile srow[f][tid].
+template <bool HAS_MISSING>
+__device__ __forceinline__ void stage_tile(float *srow, unsigned long long *tile_bar, const PredictArgs &a, int nfeat, int tid,
+                                           uint64_t r0, int nr) {
+  uint32_t *skey = reinterpret_cast<uint32_t *>(srow);  // the transposed tile holds keys, not floats
+  constexpr int B = kBlock;
+  const int ncol = a.ncol;
+  // stage 1: the tile's rows are one contiguous run of X.  Full, 16-byte aligned tiles come in with a
+  // single bulk async copy (TMA, cp.async.bulk) completing on an mbarrier — no LSU instructions, no
+  // registers; the ragged tail tile (or a misaligned matrix) falls back to a coalesced LDG/STS loop.
+  const float *__restrict__ src = a.X + r0 * (uint64_t)ncol;
+  const int n = nr * ncol;
+  const uint32_t bytes = (uint32_t)n * 4u;
+  const bool bulk = ((bytes | (uint32_t)(uintptr_t)src) & 15u) == 0u;
+  if (bulk) {
+    const uint32_t bar = (uint32_t)__cvta_generic_to_shared(tile_bar);
+    if (tid == 0) mbar_init(bar, 1);
+    __syncthreads();
+    if (tid == 0) {
+      mbar_expect_tx(bar, bytes);
+      bulk_g2s((uint32_t)__cvta_generic_to_shared(srow), src, bytes, bar);
+      // one thread polls the mbarrier; 256 threads polling the same word showed up as 1.15 G
+      // shared-memory bank-conflict wavefronts on the LSU data pipe (profiles/README.md, v4)
+      mbar_wait(bar, 0);
+    }
+    __syncthreads();
+  } else {
+    for (int i = tid; i < n; i += B) srow[i] = __ldg(src + i);
+    __syncthreads();
+  }
+  // stage 2: each thread lifts its own row into registers (stride ncol: conflict-free for the
+  // 27-column matrix), then writes it back transposed
+  float v[32];
+  const int nc32 = ncol < 32 ? ncol : 32;
+#pragma unroll
+  for (int c = 0; c < 32; ++c) v[c] = (c < nc32 && tid < nr) ? srow[tid * ncol + c] : 0.f;
+  __syncthreads();
+#pragma unroll
+  for (int c = 0; c < 32; ++c)
+    if (c < nc32) {
+      const float x = v[c];
+      uint32_t k = float_key(x);
+      if (HAS_MISSING && (x != x || x == a.missing)) k = kKeyMissing;
+      skey[c * kStride + tid] = k;
+    }
+  // columns the matrix does not have are missing (xgboost FVec::Fill leaves them flagged)
+  for (int c = nc32; c < nfeat; ++c) skey[c * kStride + tid] = kKeyMissing;
+  skey[nfeat * kStride + tid] = 0u;
+}
+
 template <int ILP, bool HAS_MISSING, bool PRED_LEAF, bool PARK, int MINB, int TEXMODE = 0, int CTOP = 0>
 __global__ void __launch_bounds__(kBlock, MINB) predict_rows_kernel(DeviceForest f, PredictArgs a) {
   extern __shared__ __align__(128) float srow[];
-  uint32_t *skey = reinterpret_cast<uint32_t *>(srow);  // the transposed tile holds keys, not floats
   __shared__ __align__(8) unsigned long long tile_bar;
   const int tid = threadIdx.x;
   constexpr int B = kBlock;
   const uint64_t r0 = (uint64_t)blockIdx.x * B;
   const uint64_t left = a.nrow - r0;
   const int nr = left < (uint64_t)B ? (int)left : B;
-  const int ncol = a.ncol;
-  {
-    // stage 1: the tile's rows are one contiguous run of X.  Full, 16-byte aligned tiles come in with a
-    // single bulk async copy (TMA, cp.async.bulk) completing on an mbarrier — no LSU instructions, no
-    // registers; the ragged tail tile (or a misaligned matrix) falls back to a coalesced LDG/STS loop.
-    const float *__restrict__ src = a.X + r0 * (uint64_t)ncol;
-    const int n = nr * ncol;
-    const uint32_t bytes = (uint32_t)n * 4u;
-    const bool bulk = ((bytes | (uint32_t)(uintptr_t)src) & 15u) == 0u;
-    if (bulk) {
-      const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&tile_bar);
-      if (tid == 0) mbar_init(bar, 1);
-      __syncthreads();
-      if (tid == 0) {
-        mbar_expect_tx(bar, bytes);
-        bulk_g2s((uint32_t)__cvta_generic_to_shared(srow), src, bytes, bar);
-        // one thread polls the mbarrier; 256 threads polling the same word showed up as 1.15 G
-        // shared-memory bank-conflict wavefronts on the LSU data pipe (profiles/README.md, v4)
-        mbar_wait(bar, 0);
-      }
-      __syncthreads();
-    } else {
-      for (int i = tid; i < n; i += B) srow[i] = __ldg(src + i);
-      __syncthreads();
-    }
-    // stage 2: each thread lifts its own row into registers (stride ncol: conflict-free for the
-    // 27-column matrix), then writes it back transposed
-    float v[32];
-    const int nc32 = ncol < 32 ? ncol : 32;
-#pragma unroll
-    for (int c = 0; c < 32; ++c) v[c] = (c < nc32 && tid < nr) ? srow[tid * ncol + c] : 0.f;
-    __syncthreads();
-#pragma unroll
-    for (int c = 0; c < 32; ++c)
-      if (c < nc32) {
-        const float x = v[c];
-        uint32_t k = float_key(x);
-        if (HAS_MISSING && (x != x || x == a.missing)) k = kKeyMissing;
-        skey[c * kStride + tid] = k;
-      }
-    // columns the matrix does not have are missing (xgboost FVec::Fill leaves them flagged)
-    for (int c = nc32; c < f.nfeat; ++c) skey[c * kStride + tid] = kKeyMissing;
-    skey[f.nfeat * kStride + tid] = 0u;
-  }
+  stage_tile<HAS_MISSING>(srow, &tile_bar, a, f.nfeat, tid, r0, nr);
   if (tid >= nr) return;
   const bool live = true;
   const uint32_t my = (uint32_t)__cvta_generic_to_shared(srow + tid);
@@ -324,6 +430,51 @@ __global__ void __launch_bounds__(kBlock, MINB) predict_rows_kernel(DeviceForest
   if (!PRED_LEAF && live) a.out[row] = export_transform(acc, a.exp10, a.scale);
 }
 
+// all trees of the forest on the two-level records: ILP-wide groups, then half-width groups (one LSU tree,
+// the rest on the texture pipe), then one by one — always in tree order (float32 sum order is part of parity)
+template <int ILP, int TEXMODE>
+__device__ __forceinline__ float forest_sum_duo(const DeviceForest &f, uint32_t my, int ntree) {
+  float acc = f.base_score;
+  int t = 0;
+  for (; t + ILP <= ntree; t += ILP) {
+    uint32_t xb[ILP];
+    walk_group_duo<ILP, TEXMODE>(f.recs, f.tex4, f.tree_depth, t, my, xb);
+#pragma unroll
+    for (int j = 0; j < ILP; ++j) acc = __fadd_rn(acc, __uint_as_float(xb[j]));
+  }
+  constexpr int H = ILP / 2;
+  if (H >= 2) {
+    for (; t + H <= ntree; t += H) {
+      uint32_t xb[H > 0 ? H : 1];
+      walk_group_duo<(H > 0 ? H : 1), ((1 << H) - 2)>(f.recs, f.tex4, f.tree_depth, t, my, xb);
+#pragma unroll
+      for (int j = 0; j < H; ++j) acc = __fadd_rn(acc, __uint_as_float(xb[j]));
+    }
+  }
+  for (; t < ntree; ++t) {
+    uint32_t xb[1];
+    walk_group_duo<1, 0>(f.recs, f.tex4, f.tree_depth, t, my, xb);
+    acc = __fadd_rn(acc, __uint_as_float(xb[0]));
+  }
+  return acc;
+}
+
+// predict_rows_kernel's clean-matrix / sums case on the two-level records
+template <int ILP, int MINB, int TEXMODE>
+__global__ void __launch_bounds__(kBlock, MINB) predict_rows_duo_kernel(DeviceForest f, PredictArgs a) {
+  extern __shared__ __align__(128) float srow[];
+  __shared__ __align__(8) unsigned long long tile_bar;
+  const int tid = threadIdx.x;
+  const uint64_t r0 = (uint64_t)blockIdx.x * kBlock;
+  const uint64_t left = a.nrow - r0;
+  const int nr = left < (uint64_t)kBlock ? (int)left : kBlock;
+  stage_tile<false>(srow, &tile_bar, a, f.nfeat, tid, r0, nr);
+  if (tid >= nr) return;
+  const uint32_t my = (uint32_t)__cvta_generic_to_shared(srow + tid);
+  const float acc = forest_sum_duo<ILP, TEXMODE>(f, my, a.ntree_used);
+  a.out[r0 + tid] = export_transform(acc, a.exp10, a.scale);
+}
+
 // ---- fused Run1 variant: the tile is assembled straight from the SoA feature fields ------------------
 // (OH_GridCompMod.F90:303-345 pack + :347 create + :356 predict + :369,:1569 transform in one kernel).
 // Row m of the slab is cell e = e0 + m; per feature the CTA's 256 cells are contiguous in the source
@@ -348,8 +499,10 @@ __device__ __forceinline__ float forest_sum(const DeviceForest &f, uint32_t my, 
   return acc;
 }
 
-template <int TEXMODE, int CTOP>
-__global__ void __launch_bounds__(kBlock, 6) predict_soa_kernel(DeviceForest f, SoaArgs a) {
+// DUO: clean tiles walk the two-level records (the constant table then holds the heap-ordered tops, so a tile
+// with missing entries walks the 8-byte nodes without a table: CTOP must be 0).
+template <int TEXMODE, int CTOP, bool DUO = false>
+__global__ void __launch_bounds__(kBlock, DUO ? kDuoMinBlocks : 6) predict_soa_kernel(DeviceForest f, SoaArgs a) {
   extern __shared__ __align__(128) float srow[];
   uint32_t *skey = reinterpret_cast<uint32_t *>(srow);
   const int tid = threadIdx.x;
@@ -388,6 +541,8 @@ __global__ void __launch_bounds__(kBlock, 6) predict_soa_kernel(DeviceForest f, 
   float acc;
   if (tile_missing)
     acc = forest_sum<4, true, true, TEXMODE, CTOP>(f, my, a.ntree_used);
+  else if (DUO)
+    acc = forest_sum_duo<kDuoIlp, kDuoTexMask>(f, my, a.ntree_used);
   else
     acc = forest_sum<4, false, true, TEXMODE, CTOP>(f, my, a.ntree_used);
   if (a.pred) a.pred[m] = acc;
@@ -402,6 +557,7 @@ cudaError_t launch_predict_soa(const DeviceForest &f, const SoaArgs &a, const Tu
   if (nblk > 0x7fffffffull) return cudaErrorInvalidConfiguration;
   const bool tex = f.tex != 0 && t.variant >= 0;
   auto k = !tex ? predict_soa_kernel<0, 0> : (f.const_top_levels == 4 ? predict_soa_kernel<0xA, 4> : predict_soa_kernel<0xA, 0>);
+  if (f.duo_ready) k = predict_soa_kernel<0xA, 0, true>;
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   k<<<dim3((unsigned)nblk), kBlock, smem, s>>>(f, a);
@@ -416,6 +572,19 @@ static cudaError_t launch_predict_one(const DeviceForest &f, const PredictArgs &
   const uint64_t nblk = (a.nrow + kBlock - 1) / kBlock;
   if (nblk > 0x7fffffffull) return cudaErrorInvalidConfiguration;
   auto k = predict_rows_kernel<ILP, HM, PL, PARK, MINB, TEXMODE, CTOP>;
+  cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  k<<<dim3((unsigned)nblk), kBlock, smem, s>>>(f, a);
+  return QC_LAUNCHED();
+}
+
+template <int ILP, int MINB, int TEXMODE>
+static cudaError_t launch_predict_duo(const DeviceForest &f, const PredictArgs &a, cudaStream_t s) {
+  const int slots = (f.nfeat + 1) > a.ncol ? (f.nfeat + 1) : a.ncol;
+  const size_t smem = (size_t)kStride * slots * sizeof(float);
+  const uint64_t nblk = (a.nrow + kBlock - 1) / kBlock;
+  if (nblk > 0x7fffffffull) return cudaErrorInvalidConfiguration;
+  auto k = predict_rows_duo_kernel<ILP, MINB, TEXMODE>;
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   k<<<dim3((unsigned)nblk), kBlock, smem, s>>>(f, a);
@@ -443,7 +612,16 @@ cudaError_t launch_predict(const DeviceForest &f, const PredictArgs &a, const Tu
     if (tex && ctop == 4) return launch_predict_one<4, true, false, true, 6, kTex, 4>(f, a, s);
     return tex ? launch_predict_one<4, true, false, true, 6, kTex>(f, a, s) : launch_predict_one<4, true, false, true, 6, 0>(f, a, s);
   }
-  // clean matrix, sums: the production path.  Experiments (qcoh_set_param): park, ilp, minb, variant, top_levels.
+  // clean matrix, sums: the production path.  Experiments (qcoh_set_param): park, ilp, minb, variant, top_levels, duo.
+  if (f.duo_ready) {  // the constant table holds this booster's heap-ordered tops (capi_xgb.cpp sync_const_top)
+    // experiment grid (qcoh_set_param duo=1 + ilp / minb / duo_mask): trees in flight x resident CTAs x which
+    // of the trees gather through the texture pipe; measurements in profiles/README.md
+#define QC_DUO(I, M, MASK) \
+  if (t.ilp == I && t.minb == M && t.duo_mask == MASK) return launch_predict_duo<I, M, MASK>(f, a, s);
+    QC_DUO(4, 6, 0xA) QC_DUO(4, 6, 0xE) QC_DUO(4, 6, 0xF) QC_DUO(3, 6, 0x6) QC_DUO(3, 6, 0x2) QC_DUO(6, 5, 0x2A) QC_DUO(8, 4, 0xEE)
+#undef QC_DUO
+    return launch_predict_duo<kDuoIlp, kDuoMinBlocks, kDuoTexMask>(f, a, s);
+  }
   if (t.park == 0) return launch_predict_one<4, false, false, false, 6, 0>(f, a, s);
   if (t.variant > 0 && f.tex) {
 #define QC_TEX(V, I, MASK)                                                                  \

@@ -14,6 +14,9 @@ struct DeviceForest {
   const int32_t *orig_id = nullptr;      // [num_nodes]
   cudaTextureObject_t tex = 0;           // the same nodes as a 1-D linear uint2 texture (TEX pipe)
   int const_top_levels = 0;              // levels of every tree currently held in the constant-memory table
+  const uint4 *recs = nullptr;           // two-level records (forest.hpp DuoForest), or nullptr
+  cudaTextureObject_t tex4 = 0;          // the records as a 1-D linear uint4 texture
+  int duo_ready = 0;                     // the constant-memory record-base table holds this booster
   int32_t ntree = 0;
   int32_t nfeat = 0;
   int32_t max_depth = 0;
@@ -41,12 +44,18 @@ struct Tunables {
   int top_levels = -1;  // tree levels served from constant memory: -1 = default (4), 0 = none
   int park = -1;     // -1 = default (on)
   int minb = 0;      // min resident CTAs per SM the kernel is compiled for (register budget)
+  int duo = -1;      // two-level records: -1 = default, 0 = off, 1 = on
+  int duo_mask = 0;  // (experiment) texture-pipe tree mask of the two-level kernel, 0 = default
 };
+
+constexpr bool kDuoDefault = true;  // two-level records by default when the booster qualifies
 
 uint64_t launch_count();
 
 // (experiment) copy levels 0..levels-1 of every tree into the kernel's __constant__ table
 cudaError_t upload_const_top(const uint32_t *dev_nodes_xy, const uint32_t *tree_offset, int ntree, int levels, cudaStream_t s);
+// two-level layout: DuoForest::top_xy into the tree-top table and DuoForest::tree_slot into its base table
+cudaError_t upload_const_duo(const uint32_t *top_xy, const uint32_t *tree_slot, int ntree, cudaStream_t s);
 
 // flags[0] |= 1 if any entry is NaN or == missing; flags[0] |= 2 if any entry is +-inf
 // (and `missing` is finite) — what XGDMatrixCreateFromMat checks (xgboost src/data/data.cc).

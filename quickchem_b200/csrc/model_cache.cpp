@@ -74,7 +74,8 @@ Booster *cache_get(const std::string &fname) {
   std::unique_ptr<Booster> b(new Booster());
   HostForest hf = load_model_file(fname.c_str());
   FlatForest ff = flatten(hf);
-  b->host = std::move(hf), b->flat = std::move(ff);
+  DuoForest df = build_duo(ff, hf.num_feature);
+  b->host = std::move(hf), b->flat = std::move(ff), b->duo = std::move(df);
   b->loaded = true, b->uploaded = false;
   b->version = ++g_version_counter;
   b->cache_owned = true;  // uploaded at first use (qcoh_oh_set_booster / predict), like qcoh_booster_parse

@@ -23,6 +23,15 @@ def capi():
     return m
 
 
+@pytest.fixture(params=[0, 1], ids=["nodes8", "duo"])
+def duo_mode(request, capi):
+    """Run a GPU test twice: on the 8-byte depth-ordered nodes only (duo=0), and with the two-level records
+    forced on for every clean-matrix launch (duo=1).  Both must match the oracle bit for bit."""
+    capi.set_param("duo", request.param)
+    yield request.param
+    capi.set_param("duo", -1)
+
+
 @pytest.fixture(scope="session")
 def oracle():
     from oracle import cpu

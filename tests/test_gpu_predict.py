@@ -10,7 +10,7 @@ import pytest
 from conftest import inject_specials
 from quickchem_b200 import synth, xgbmodel
 
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu, pytest.mark.usefixtures("duo_mode")]
 
 REL_TOL_OH = 1e-6  # BASELINE.json north_star: summed OH within max relative error 1e-6
 
@@ -219,6 +219,22 @@ def test_kernel_variants_agree(capi, oracle, small_model_path, small_forest):
                 capi.set_param("variant", variant)
                 assert np.array_equal(b.predict(d).view(np.uint32), ref.view(np.uint32)), (top, variant)
         capi.set_param("variant", 0)
+        capi.set_param("top_levels", -1)
+        # two-level records: default shape and the experiment grid (an unknown combination runs the default)
+        capi.set_param("duo", 1)
+        for ilp, minb, mask in ((0, 0, 0), (4, 6, 0xA), (4, 6, 0xE), (4, 6, 0xF), (3, 6, 0x6), (3, 6, 0x2), (6, 5, 0x2A),
+                                (8, 4, 0xEE), (5, 5, 0x1)):  # fmt: skip
+            capi.set_param("ilp", ilp)
+            capi.set_param("minb", minb)
+            capi.set_param("duo_mask", mask)
+            assert np.array_equal(b.predict(d).view(np.uint32), ref.view(np.uint32)), ("duo", ilp, minb, mask)
+            for nt in (1, 5, 7, 11):  # group remainders: 6-wide, 3-wide, single
+                assert np.array_equal(b.predict(d, ntree_limit=nt).view(np.uint32),
+                                      oracle.Model(small_model_path).predict(x, ntree_limit=nt).view(np.uint32)), (ilp, nt)
+        capi.set_param("ilp", 0)
+        capi.set_param("minb", 0)
+        capi.set_param("duo_mask", 0)
+        capi.set_param("duo", -1)
         xm = inject_specials(x, small_forest, np.random.default_rng(5))  # the has-missing build with the table
         refm = oracle.Model(small_model_path).predict(xm)
         for top in (0, 4):
@@ -230,6 +246,8 @@ def test_kernel_variants_agree(capi, oracle, small_model_path, small_forest):
         capi.set_param("park", -1)
         capi.set_param("variant", 0)
         capi.set_param("top_levels", -1)
+        capi.set_param("duo_mask", 0)
+        capi.set_param("duo", -1)
 
 
 def test_pipelined_create_matches_plain_path(capi, oracle, tmp_path, small_model_path, small_forest):
@@ -298,8 +316,8 @@ def test_dmatrix_file_roundtrip(capi, tmp_path, small_model_path):
 
 
 def test_more_trees_than_the_constant_table_holds(capi, oracle, tmp_path):
-    """The constant-memory table of tree tops holds 8000 nodes (500 trees x 16); a bigger forest must run
-    without it and still match."""
+    """The constant-memory table of tree tops holds 7680 nodes (480 trees x 16); a bigger forest must run
+    without it (and without the two-level records, which need the table) and still match."""
     rng = np.random.default_rng(8)
     trees = [xgbmodel.tree_from_nested((int(rng.integers(27)), float(rng.normal()), bool(rng.random() < 0.5),
                                         float(rng.normal()), (int(rng.integers(27)), float(rng.normal()), False, 1.0, -1.0)))

@@ -9,7 +9,7 @@ import pytest
 
 from quickchem_b200 import synth
 
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu, pytest.mark.usefixtures("duo_mode")]
 REL_TOL_OH = 1e-6
 
 

@@ -260,3 +260,75 @@ def test_model_cache_without_gpu(capi):
     assert capi.model_cache_size() == 2
     capi.model_cache_clear()
     assert capi.model_cache_size() == 0
+
+
+def _key(v):
+    b = (np.asarray(v, np.float32) + np.float32(0)).view(np.uint32)
+    return b ^ np.where(b >> 31, np.uint32(0xFFFFFFFF), np.uint32(0x80000000))
+
+
+def _duo_walk(rec, tslot, top, t, x, nfeat, max_depth):
+    """The device algorithm of walk_group_duo restated in numpy: 4 levels on the complete heap-ordered top,
+    then one 16-byte record per two levels.  Returns (leaf value bits, XGBoost node id) per row."""
+    n = len(x)
+    ar = np.arange(n)
+    kx = np.concatenate([_key(x), np.zeros((n, 1), np.uint32)], axis=1).astype(np.uint64)  # slot nfeat: key 0
+    hi = np.ones(n, np.int64)
+    for _ in range(4):
+        tx, tf = top[t, hi, 0].astype(np.uint64), (top[t, hi, 1] >> 26).astype(np.int64)
+        hi = 2 * hi + ((tx + kx[ar, tf]) >> 32).astype(np.int64)
+    s = hi - 16 + int(tslot[t])
+    walking = np.ones(n, bool)
+    val, nid = np.zeros(n, np.uint32), np.zeros(n, np.uint32)
+    d = 4
+    while d <= max(max_depth, 3) + 1:
+        r = rec[s]
+        m = r[:, 3].astype(np.int64)
+        r1 = ((r[:, 0].astype(np.uint64) + kx[ar, m & 31]) >> 32).astype(np.int64)
+        xs = np.where(r1 == 1, r[:, 2], r[:, 1]).astype(np.uint64)
+        ms = np.where(r1 == 1, m << 5, m)
+        r2 = ((xs + kx[ar, (ms >> 10) & 31]) >> 32).astype(np.int64)
+        blk = m >> 15
+        term = walking & (blk == 0)
+        val, nid = np.where(term, r[:, 0], val), np.where(term, r[:, 1], nid)
+        walking &= blk != 0
+        s = np.where(walking, int(tslot[t]) + blk * 4 + 2 * r1 + r2, s)
+        d += 2
+    assert not walking.any()
+    return val, nid
+
+
+def test_two_level_records_walk_like_the_flat_nodes(capi, tmp_path, small_forest):
+    """forest.cpp::build_duo: the two-level record layout (complete heap-ordered tops with padded shallow
+    leaves + 16-byte records) must land every row in the same leaf as the depth-ordered 8-byte nodes — for grown
+    trees, stumps, single leaves and values exactly on thresholds."""
+    rng = np.random.default_rng(11)
+    stumpy = xgbmodel.Forest(
+        trees=[xgbmodel.tree_from_nested(1.5), xgbmodel.tree_from_nested((3, 0.5, True, -1.0, 2.0)),
+               xgbmodel.tree_from_nested((0, 0.0, False, (1, 0.25, True, 10.0, 20.0), (2, -0.0, False, 30.0, 40.0))),
+               xgbmodel.tree_from_nested((5, 0.1, True, (6, 0.2, True, (7, 0.3, True, (8, 0.4, False, (9, 0.5, True, 1.0, 2.0), 3.0), 4.0), 5.0), 6.0))],
+        base_score=0.0, num_feature=27)  # fmt: skip
+    deep = synth.random_forest_structure(5, 13, seed=4)
+    for name, forest in (("small", small_forest), ("stumpy", stumpy), ("deep", deep)):
+        p = str(tmp_path / f"{name}.model")
+        xgbmodel.write_legacy_binary(forest, p)
+        b = capi.Booster(p, parse_only=True)
+        nodes, off, depth, orig = b.flat()
+        rec, tslot, top = b.duo()
+        assert rec.shape[1] == 4 and np.all(tslot % 8 == 0)  # tree bases on 128-byte lines
+        x = rng.normal(0, 1, (3000, 27)).astype(np.float32)
+        thr = nodes[:, 0].view(np.float32)
+        internal = np.nonzero(nodes[:, 1] & ((1 << 23) - 1))[0]
+        for i in rng.choice(internal, min(len(internal), 300), replace=False):  # rows exactly on thresholds
+            x[rng.integers(len(x)), int(nodes[i, 1] >> 26)] = thr[i]
+        xs = np.concatenate([x, np.full((len(x), 1), -np.inf, np.float32)], axis=1)
+        feat, rel = (nodes[:, 1] >> 26).astype(np.int64), (nodes[:, 1] & ((1 << 23) - 1)).astype(np.int64)
+        ar = np.arange(len(x))
+        for t in range(len(off) - 1):
+            idx = np.full(len(x), off[t], np.int64)
+            for _ in range(int(depth[t]) + 1):
+                right = ~(xs[ar, feat[idx]] < thr[idx])
+                idx = np.where(rel[idx] != 0, idx + rel[idx] + right, idx)
+            val, nid = _duo_walk(rec, tslot, top, t, x, 27, int(depth[t]))
+            assert np.array_equal(val, nodes[idx, 0]), (name, t)
+            assert np.array_equal(nid, orig[idx].astype(np.uint32)), (name, t)
