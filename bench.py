@@ -386,14 +386,15 @@ def main():
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args.grid, world),
         "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
-        "roofline": {"bound": "hbm", "kernel": "predict_rows_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "roofline": {"bound": "hbm", "kernel": "predict_rows_duo_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic, "traffic_unit": "bytes/launch", "traffic_source": traffic_src,
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured copy)" if peaks else "fallback 6.65 TB/s",
                      "algorithmic_bytes_per_cell": ALGO_BYTES_PER_CELL, "cells_per_launch": ncell,
                      "compute_side": {"node_visits_per_cell": round(visits, 1), "node_visits_per_s_per_gpu": ncell * visits / (ms_step * 1e-3),
-                                      "note": "one visit = one 8-byte node gather + one feature fetch + compare; "
-                                              "12.75 SASS instructions per visit, issue slots 78 % busy (profiles/README.md)"},
-                     "note": "traversal is bound by the L1TEX data pipe (node gathers), not HBM: ncu l1tex 92 %, DRAM 1.3 % (profiles/README.md)"},
+                                      "note": "one visit = one tree level of one row; a 16-byte record gather decides two of them; "
+                                              "12.9 thread-instructions per visit, issue slots 75 % busy (profiles/README.md)"},
+                     "note": "traversal is bound by the L1TEX data pipes (record gathers + feature fetches), not HBM: ncu LSU 86 % / TEX 78 % "
+                             "wavefronts, DRAM 1.9 % (profiles/README.md)"},
         "cpu_baseline": cpu,
         "run1": {"value": total_cells / (ms_run1 * 1e-3), "unit": "cells/s", "ms_per_step": ms_run1,
                  "what": "fused device-resident Run1: assembly + predict + export transform + diagnostic"

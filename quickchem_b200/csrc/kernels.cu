@@ -274,17 +274,17 @@ __device__ __forceinline__ void walk_group_duo(const uint4 *__restrict__ recs, c
           r[j] = __ldg(recs + idx[j]);
       }
     }
-    uint32_t kv[ILP], right1[ILP];
+    uint32_t kv0[ILP], kv[ILP], right1[ILP];
 #pragma unroll
     for (int j = 0; j < ILP; ++j) {
       // srow[feat(root)][tid]: feat is the low 5 bits of w3; one AND + one multiply-add
       uint32_t sa;
       asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(sa) : "r"(r[j].w & 31u), "r"((uint32_t)(kStride * 4)), "r"(my_saddr));
-      asm volatile("ld.shared.u32 %0, [%1];" : "=r"(kv[j]) : "r"(sa));
+      asm volatile("ld.shared.u32 %0, [%1];" : "=r"(kv0[j]) : "r"(sa));
     }
 #pragma unroll
     for (int j = 0; j < ILP; ++j) {
-      right1[j] = add_carry_out(r[j].x, kv[j]);
+      right1[j] = add_carry_out(r[j].x, kv0[j]);
       // feat(left) sits at bits 14..10 — already feat * 1024 —, feat(right) at 9..5
       const uint32_t ms = right1[j] ? (r[j].w << 5) : r[j].w;
       asm volatile("ld.shared.u32 %0, [%1];" : "=r"(kv[j]) : "r"(my_saddr + (ms & (31u << 10))));
@@ -292,9 +292,13 @@ __device__ __forceinline__ void walk_group_duo(const uint4 *__restrict__ recs, c
 #pragma unroll
     for (int j = 0; j < ILP; ++j) {
       const uint32_t xs = right1[j] ? r[j].z : r[j].y;
-      const uint32_t blk = r[j].w >> kDuoBlkShift;
+      // blk = w3 >> 15 as a multiply-high: the FMA pipe has room, the ALU pipe (SEL / LOP3 / IADD3) does not
+      uint32_t blk;
+      asm("mul.hi.u32 %0, %1, %2;" : "=r"(blk) : "r"(r[j].w), "r"(1u << (32 - kDuoBlkShift)));
       // next record = base + blk * 4 + 2 * right1 + right2
-      const uint32_t half = blk + blk + right1[j];
+      // half = 2 * blk + right1, the carry of the root compare folded into a multiply-add (FMA pipe again)
+      uint32_t half;
+      asm("{\n\t.reg .u32 t;\n\tadd.cc.u32 t, %1, %2;\n\tmadc.lo.u32 %0, %3, 2, 0;\n\t}" : "=r"(half) : "r"(r[j].x), "r"(kv0[j]), "r"(blk));
       idx[j] = step_index(c_duo_base[t + j] + half, half, xs, kv[j]);
       walking[j] = blk;  // 0: this was a terminal record, r[j].x is the leaf value
       asm volatile("" : "+r"(walking[j]));
