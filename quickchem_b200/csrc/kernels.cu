@@ -3,6 +3,9 @@
 //   K2  predict_rows_kernel   tree-ensemble traversal, replaces libxgboost's CPUPredictor behind
 //                             XGBoosterPredict (reference call site OH_GridCompMod.F90:356) with the
 //                             export transform 10**x * OHscale (:369,:1569) fused as epilogue
+//   K2b predict_rows_duo_kernel   the same on two-level 16-byte records (one gather per two tree levels):
+//                             the default for sums over a matrix without missing entries
+//       predict_soa_kernel    K2 / K2b with the tile assembled straight from the Run1 SoA fields
 //   K3  scan_matrix_kernel    the missing / inf scan of XGDMatrixCreateFromMat (:347)
 //   K1  oh_state / oh_sums / oh_pack    Run1 feature assembly (:1240-1257, :1441-1488, :303-345)
 //   K5  oh_finalize           troposphere mask + unit conversion (:1579-1595)
