@@ -231,7 +231,7 @@ int qcoh_oh_get_booster(qcoh_oh_handle h, BoosterHandle *out);
 int qcoh_expand_template(const char *pattern, int nymd, int nhms, char *out, size_t cap);
 /* Process-wide cache of parsed + uploaded boosters keyed by file name: the first request for a name loads
  * it, later ones return the same handle.  Handles belong to the cache (XGBoosterFree on one fails); a month
- * of the production forest is ~20 MB of HBM, so all twelve stay resident. */
+ * of the production forest is ~30 MB of HBM (both node layouts), so all twelve stay resident. */
 int qcoh_model_cache_get(const char *fname, BoosterHandle *out);
 int qcoh_model_cache_size(void);
 /* Frees every cached booster; handles obtained from the cache (and fused-Run1 handles using them) die. */
