@@ -309,17 +309,23 @@ def test_two_level_records_walk_like_the_flat_nodes(capi, tmp_path, small_forest
                xgbmodel.tree_from_nested((5, 0.1, True, (6, 0.2, True, (7, 0.3, True, (8, 0.4, False, (9, 0.5, True, 1.0, 2.0), 3.0), 4.0), 5.0), 6.0))],
         base_score=0.0, num_feature=27)  # fmt: skip
     deep = synth.random_forest_structure(5, 13, seed=4)
-    for name, forest in (("small", small_forest), ("stumpy", stumpy), ("deep", deep)):
+    # many shapes: bushy and shallow, sparse and deep (long chains with leaf children at odd and even depths), few
+    # and many features, wide and narrow threshold ranges
+    shapes = [(f"rand{i}", synth.random_forest_structure(6, d, num_feature=nf, seed=100 + i, p_leaf=pl, thr_scale=ts))
+              for i, (d, pl, nf, ts) in enumerate(((3, 0.0, 27, 1.0), (4, 0.3, 27, 1.0), (5, 0.5, 5, 0.2), (9, 0.05, 27, 1.0),
+                                                   (16, 0.35, 27, 3.0), (20, 0.45, 31, 1.0), (24, 0.48, 1, 1.0)))]  # fmt: skip
+    for name, forest in [("small", small_forest), ("stumpy", stumpy), ("deep", deep)] + shapes:
         p = str(tmp_path / f"{name}.model")
         xgbmodel.write_legacy_binary(forest, p)
         b = capi.Booster(p, parse_only=True)
         nodes, off, depth, orig = b.flat()
         rec, tslot, top = b.duo()
         assert rec.shape[1] == 4 and np.all(tslot % 8 == 0)  # tree bases on 128-byte lines
-        x = rng.normal(0, 1, (3000, 27)).astype(np.float32)
+        nf = forest.num_feature
+        x = rng.normal(0, 1, (3000, nf)).astype(np.float32)
         thr = nodes[:, 0].view(np.float32)
         internal = np.nonzero(nodes[:, 1] & ((1 << 23) - 1))[0]
-        for i in rng.choice(internal, min(len(internal), 300), replace=False):  # rows exactly on thresholds
+        for i in rng.choice(internal, min(len(internal), 300), replace=False) if len(internal) else ():  # on thresholds
             x[rng.integers(len(x)), int(nodes[i, 1] >> 26)] = thr[i]
         xs = np.concatenate([x, np.full((len(x), 1), -np.inf, np.float32)], axis=1)
         feat, rel = (nodes[:, 1] >> 26).astype(np.int64), (nodes[:, 1] & ((1 << 23) - 1)).astype(np.int64)
@@ -329,6 +335,6 @@ def test_two_level_records_walk_like_the_flat_nodes(capi, tmp_path, small_forest
             for _ in range(int(depth[t]) + 1):
                 right = ~(xs[ar, feat[idx]] < thr[idx])
                 idx = np.where(rel[idx] != 0, idx + rel[idx] + right, idx)
-            val, nid = _duo_walk(rec, tslot, top, t, x, 27, int(depth[t]))
+            val, nid = _duo_walk(rec, tslot, top, t, x, nf, int(depth[t]))
             assert np.array_equal(val, nodes[idx, 0]), (name, t)
             assert np.array_equal(nid, orig[idx].astype(np.uint32)), (name, t)
