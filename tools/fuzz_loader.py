@@ -1,6 +1,6 @@
 """Mutate model files (truncate / flip / insert / overwrite length fields) and feed them to the loaders: every
 file must be accepted or rejected with an error, never crash.  python tools/fuzz_loader.py [seed] [iterations]"""
-import numpy as np, os, sys, tempfile
+import numpy as np, os, shutil, sys, tempfile
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from quickchem_b200 import capi, synth, xgbmodel
 f = synth.random_forest_structure(3, 4, seed=2)
@@ -28,4 +28,5 @@ for ext in ('model','json','ubj'):
             bo = capi.Booster(p, parse_only=True); bo.info(); bo.flat(); n_ok+=1
         except capi.QcohError:
             n_err+=1
+shutil.rmtree(d, ignore_errors=True)
 print('ok', n_ok, 'rejected', n_err)
