@@ -245,6 +245,22 @@ int qcoh_oh_select_model(qcoh_oh_handle h, const char *pattern, int nymd, int nh
  * "OH_boost";  2-D [ncol]: "LAT" "SZA" "stratO3".  out may be host or device memory. */
 int qcoh_oh_get_diag(qcoh_oh_handle h, const char *name, float *out);
 
+/* ---- Run1 control: the host-side decisions around the fused call -------------------- */
+/* OH_data_source (OH_GridCompMod.F90:31-33, rc key `OH_data_source`, OH_instance_OH.rc:24). */
+enum { QCOH_PRECOMPUTED = 1, QCOH_ONLINE_INST = 2, QCOH_ONLINE_AVG24 = 3 };
+/* "PRECOMPUTED" / "ONLINE_INST" / "ONLINE_AVG24" -> 1 / 2 / 3 (:551-553); -1 for anything else. */
+int qcoh_data_source_from_name(const char *token);
+/* :1189-1193 — qcoh_run1_in.need_to_call_boost: with compute_once_per_day only the step at hhmmss == 0 boosts. */
+int qcoh_need_to_call_boost(int compute_once_per_day, int nhms);
+/* :1307-1320 — the 24-hour-average spin-up switch: ONLINE_AVG24 and T_avg24(1,1,1) == 0.0. */
+int qcoh_use_inst_values(int data_source, float t_avg24_first);
+/* Which import feeds a boost-state field (:1326-1548).  field: "T" "Q" "PLE" "ZLE" "TAUCLW" "TAUCLI" "CH4" "CO"
+ * "FCLD" and "BCSCACOEF".."NISCACOEF" follow OH_data_source ("oh_X" / "X" / "X_avg24", or "X" during spin-up);
+ * the climatological ones ("NO2" .. "CH2O", "ALBUV", "GMITO3", "GMITTO3", "OH") are always "oh_X"; "T_MOD" "Q_MOD"
+ * "PLE_MOD" "TROPP" are the current model state "T" "Q" "PLE" "TROPP".  *is_4d (may be NULL) = 1 when the import
+ * carries a wavelength axis (online scattering coefficients, sliced at wavelength_index, :1456-1465). */
+int qcoh_import_name(const char *field, int data_source, int use_inst_values, char *out, size_t cap, int *is_4d);
+
 /* ---- host mirror of the reference driver -------------------------------------------- */
 /* C mirror of `predict_OH_with_XGB` (OH_GridCompMod.F90:123-398): same arguments in the same
  * order, arrays as Fortran lays them out; bb = the 27 OH_BOOST_INPUT_DATA pointers (:82-114) in

@@ -73,7 +73,8 @@ QCOH_SYMBOLS = ("qcoh_version", "qcoh_device_count", "qcoh_set_device", "qcoh_ho
                 "qcoh_oh_run1", "qcoh_oh_free", "qcoh_oh_get_diag", "qcoh_predict_OH_with_XGB", "qcoh_predict_OH_reset",
                 "qcoh_predict_OH_reload_on_file_change", "qcoh_oh_set_booster", "qcoh_oh_get_booster",
                 "qcoh_expand_template", "qcoh_model_cache_get", "qcoh_model_cache_size", "qcoh_model_cache_clear",
-                "qcoh_oh_select_model",
+                "qcoh_oh_select_model", "qcoh_data_source_from_name", "qcoh_need_to_call_boost", "qcoh_use_inst_values",
+                "qcoh_import_name",
                 "qcoh_partition_columns", "qcoh_comm_get_unique_id", "qcoh_comm_init",
                 "qcoh_comm_allreduce_sum_f64", "qcoh_comm_destroy")  # fmt: skip
 
@@ -136,6 +137,10 @@ def lib():
         L.qcoh_expand_template.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_char_p, C.c_size_t]
         L.qcoh_model_cache_get.argtypes = [C.c_char_p, C.POINTER(vp)]
         L.qcoh_oh_select_model.argtypes = [vp, C.c_char_p, C.c_int, C.c_int, C.POINTER(C.c_int)]
+        L.qcoh_data_source_from_name.argtypes = [C.c_char_p]
+        L.qcoh_need_to_call_boost.argtypes = [C.c_int, C.c_int]
+        L.qcoh_use_inst_values.argtypes = [C.c_int, C.c_float]
+        L.qcoh_import_name.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_char_p, C.c_size_t, C.POINTER(C.c_int)]
         L.qcoh_predict_OH_reload_on_file_change.argtypes = [C.c_int]
         L.qcoh_predict_OH_reload_on_file_change.restype = None
         _LIB = L
@@ -296,6 +301,13 @@ def expand_template(pattern: str, nymd: int, nhms: int = 0) -> str:
     buf = C.create_string_buffer(4096)
     check(lib().qcoh_expand_template(os.fsencode(pattern), nymd, nhms, buf, C.c_size_t(len(buf))))
     return os.fsdecode(buf.value)
+
+
+def import_name(field: str, data_source: int, use_inst_values: bool = False):
+    """(import name, is_4d) feeding a boost-state field (OH_GridCompMod.F90:1326-1548)."""
+    buf, four_d = C.create_string_buffer(64), C.c_int(0)
+    check(lib().qcoh_import_name(field.encode(), data_source, int(use_inst_values), buf, len(buf), C.byref(four_d)))
+    return buf.value.decode(), bool(four_d.value)
 
 
 def model_cache_size() -> int:

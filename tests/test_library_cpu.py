@@ -338,3 +338,34 @@ def test_two_level_records_walk_like_the_flat_nodes(capi, tmp_path, small_forest
             val, nid = _duo_walk(rec, tslot, top, t, x, nf, int(depth[t]))
             assert np.array_equal(val, nodes[idx, 0]), (name, t)
             assert np.array_equal(nid, orig[idx].astype(np.uint32)), (name, t)
+
+
+def test_run1_control_decisions(capi):
+    """Host-side decisions around the fused call, restated from OH_GridCompMod.F90: boost alarm (:1189-1193),
+    24-hour-average spin-up switch (:1307-1320), import selection per OH_data_source (:1326-1548)."""
+    L = capi.lib()
+    assert [L.qcoh_data_source_from_name(t) for t in (b"PRECOMPUTED", b"ONLINE_INST", b"ONLINE_AVG24", b"online", b"")] == [1, 2, 3, -1, -1]
+    # compute_once_per_day: only the 00:00:00 step boosts; otherwise every alarmed step does
+    assert [L.qcoh_need_to_call_boost(1, hms) for hms in (0, 1, 3000, 120000, 233000)] == [1, 0, 0, 0, 0]
+    assert [L.qcoh_need_to_call_boost(0, hms) for hms in (0, 3000, 120000)] == [1, 1, 1]
+    # spin-up: ONLINE_AVG24 and an all-zero daily mean (first element of T_avg24)
+    assert L.qcoh_use_inst_values(3, 0.0) == 1 and L.qcoh_use_inst_values(3, 251.5) == 0
+    assert L.qcoh_use_inst_values(1, 0.0) == 0 and L.qcoh_use_inst_values(2, 0.0) == 0
+    sel = ("T", "Q", "PLE", "ZLE", "TAUCLW", "TAUCLI", "CH4", "CO", "FCLD")
+    sca = ("BCSCACOEF", "OCSCACOEF", "BRSCACOEF", "DUSCACOEF", "SUSCACOEF", "SSSCACOEF", "NISCACOEF")
+    for f in sel + sca:
+        four_d = f in sca
+        assert capi.import_name(f, 1) == ("oh_" + f, False)  # PRECOMPUTED: 3-D climatology, also for SCACOEF (:1388)
+        assert capi.import_name(f, 2) == (f, four_d)
+        assert capi.import_name(f, 3, use_inst_values=False) == (f + "_avg24", four_d)
+        assert capi.import_name(f, 3, use_inst_values=True) == (f, four_d)
+        assert capi.import_name(f, 1, use_inst_values=True) == ("oh_" + f, False)  # the switch only matters for AVG24
+    for f in ("NO2", "O3", "ISOP", "ACET", "C2H6", "C3H8", "PRPE", "ALK4", "MP", "H2O2", "CH2O", "ALBUV", "GMITO3", "GMITTO3", "OH"):
+        for src in (1, 2, 3):
+            assert capi.import_name(f, src) == ("oh_" + f, False)
+    assert [capi.import_name(f, 3)[0] for f in ("T_MOD", "Q_MOD", "PLE_MOD", "TROPP")] == ["T", "Q", "PLE", "TROPP"]
+    for bad_field, src in (("SZA", 1), ("T", 0), ("T", 4), ("", 2)):
+        with pytest.raises(capi.QcohError, match="qcoh_import_name"):
+            capi.import_name(bad_field, src)
+    buf = ctypes.create_string_buffer(4)
+    assert L.qcoh_import_name(b"TAUCLW", 3, 0, buf, 4, None) == -1  # "TAUCLW_avg24" does not fit
