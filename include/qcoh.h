@@ -129,10 +129,12 @@ int qcoh_booster_get_flat(BoosterHandle handle, const uint32_t **nodes_xy, const
 
 /* Two-level records (DESIGN.md "Two levels per gather"), for inspection/tests: 16-byte records
  * {w0, w1, w2, w3}; tree_slot[num_trees] = first record of each tree; top_xy[num_trees][16][2] = the complete
- * heap-ordered levels 0..3 that go to constant memory.  Fails (-1, reason in XGBGetLastError) when the
- * booster does not qualify (> 2^17 record blocks in a tree). */
+ * heap-ordered levels 0..3 that go to constant memory.  w3 = blk << blk_shift | ... (forest.hpp): blk_shift = 18
+ * when the records carry the three default-direction bits (every tree < 2^14 record blocks), else 15.  Fails
+ * (-1, reason in XGBGetLastError) when the booster does not qualify (> 2^17 record blocks in a tree). */
 int qcoh_booster_get_duo(BoosterHandle handle, const uint32_t **rec, const uint32_t **tree_slot, const uint32_t **top_xy,
                          int64_t *num_slots);
+int qcoh_booster_get_duo_info(BoosterHandle handle, int *blk_shift, int *has_default_bits);
 
 /* ---- device-resident predict -------------------------------------------------------- */
 /* A DMatrix whose storage is allocated in HBM and filled by the caller (device pointer
@@ -142,6 +144,9 @@ int qcoh_dmatrix_create_device(bst_ulong nrow, bst_ulong ncol, float missing, DM
 int qcoh_dmatrix_device_ptr(DMatrixHandle handle, float **out_dev);
 int qcoh_dmatrix_upload(DMatrixHandle handle, const float *host_rows, bst_ulong row0, bst_ulong nrows);
 int qcoh_dmatrix_seal(DMatrixHandle handle);
+/* The device form of a sealed matrix (what the predict kernels read): order-preserving integer keys in
+ * feature-major tiles of 256 rows, Xt[tile][col][256] uint32 (DESIGN.md "Data layout"); for inspection / tests. */
+int qcoh_dmatrix_tiles_ptr(DMatrixHandle handle, const uint32_t **out_dev, uint64_t *num_tiles);
 
 /* Export transform fused into the predict kernel's epilogue (OH_GridCompMod.F90:369,1569):
  * out = scale * 10**pred when exp10 != 0, else the raw prediction. */
@@ -157,6 +162,13 @@ int qcoh_booster_predict_device(BoosterHandle handle, DMatrixHandle dmat, int op
 int qcoh_set_param(const char *name, const char *value);
 /* How many kernels the library has launched since load (for bench.py's gpu_launches). */
 uint64_t qcoh_launch_count(void);
+/* Which kernel family served a prediction — what the parity tests assert.  Families: "duo" (two-level records),
+ * "nodes8" (8-byte depth-ordered nodes), each with the suffixes "_missing" (matrix with missing entries) and
+ * "_leaf" (option_mask = 2), e.g. "duo_missing_leaf"; "soa_duo" / "soa_nodes8" (fused Run1); "seal_tiles".
+ * qcoh_kernel_launches counts launches of one family since load; qcoh_last_predict_kernel names the family of the
+ * last XGBoosterPredict-side launch ("" before the first). */
+uint64_t qcoh_kernel_launches(const char *family);
+const char *qcoh_last_predict_kernel(void);
 
 /* ---- fused Run1 (feature assembly -> predict -> export transform) -------------------- */
 typedef void *qcoh_oh_handle;
@@ -239,11 +251,17 @@ int qcoh_model_cache_clear(void);
 /* expand + cache_get + qcoh_oh_set_booster in one call: what a patched Run1 calls before a boost step when
  * `reload_model_on_month_change` is on.  *changed (may be NULL) is set to 1 when the booster was switched. */
 int qcoh_oh_select_model(qcoh_oh_handle h, const char *pattern, int nymd, int nhms, int *changed);
-/* Diagnostic exports (OH_GridCompMod.F90:1602-1735, OH_StateSpecs.rc:41-73): copy one derived field of
- * the last boost step out of HBM.  name (case-sensitive, the DIAG_ suffix of the reference's export):
- * 3-D [km][ncol]: "TAUCLWDN" "TAUCLIDN" "TAUCLIUP" "TAUCLWUP" "AODUP" "AODDN" "PL" (PL_MOD, Pa) "NDWET"
- * "OH_boost";  2-D [ncol]: "LAT" "SZA" "stratO3".  out may be host or device memory. */
+/* Diagnostic exports (OH_GridCompMod.F90:1602-1735, OH_StateSpecs.rc:41-73): copy one derived field out of HBM.
+ * name (case-sensitive, the DIAG_ suffix of the reference's export).  Of the LAST BOOST step, 3-D [km][ncol]:
+ * "TAUCLWDN" "TAUCLIDN" "TAUCLIUP" "TAUCLWUP" "AODUP" "AODDN" "AOD" "PL" (bb%PL = PL_BST, from the PLE handed to
+ * boost, Pa, :1488,:1666) "OH_boost"; 2-D [ncol]: "LAT" "SZA" "stratO3".  Of the CURRENT step (the reference
+ * exports DIAG_NDWET on every alarmed step, :1598-1599): "NDWET", and "PL_MOD" (not a reference export).
+ * out may be host or device memory. */
 int qcoh_oh_get_diag(qcoh_oh_handle h, const char *name, float *out);
+/* The noon SZA (OH_GridCompMod.F90:401-466) is cached per day of year and grid (addresses, size and a hash of a
+ * strided sample of LATS / LONS).  A host that rewrites its coordinate arrays in place calls this to force a
+ * recomputation at the next boost step. */
+int qcoh_oh_invalidate_sza(qcoh_oh_handle h);
 
 /* ---- Run1 control: the host-side decisions around the fused call -------------------- */
 /* OH_data_source (OH_GridCompMod.F90:31-33, rc key `OH_data_source`, OH_instance_OH.rc:24). */

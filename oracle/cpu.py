@@ -58,11 +58,48 @@ class Run1Out(C.Structure):
                 ("pred", f32p), ("k1", C.c_int)]  # fmt: skip
 
 
+def _cpu_id() -> str:
+    """The host CPU as far as -march=native cares: model name + ISA flags."""
+    try:
+        model = flags = ""
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name") and not model:
+                model = line.split(":", 1)[1].strip()
+            if line.startswith("flags") and not flags:
+                flags = line.split(":", 1)[1].strip()
+            if model and flags:
+                break
+        import hashlib
+
+        return model + " " + hashlib.sha1(flags.encode()).hexdigest()[:12]
+    except OSError:
+        return "unknown"
+
+
+def build_flags() -> str:
+    try:
+        return subprocess.check_output(["make", "-s", "-C", _HERE, "flags"], text=True).strip()
+    except (OSError, subprocess.CalledProcessError):
+        return "unknown"
+
+
 def build(force=False):
+    """Compile the C restatement (-O3 -march=native).  The built library travels to the GPU box with the repo
+    snapshot; it is rebuilt there if that box's CPU is not the one it was built for."""
     so = os.path.join(_HERE, "libqc_oracle.so")
     src = os.path.join(_HERE, "qc_oracle.c")
-    if force or not os.path.exists(so) or (os.path.exists(src) and os.path.getmtime(src) > os.path.getmtime(so)):
+    stamp = os.path.join(_HERE, ".cpu_stamp")
+    cpu = _cpu_id()
+    try:
+        built_for = open(stamp).read()
+    except OSError:
+        built_for = ""
+    stale = not os.path.exists(so) or any(os.path.exists(f) and os.path.getmtime(f) > os.path.getmtime(so)
+                                          for f in (src, os.path.join(_HERE, "Makefile")))  # fmt: skip
+    if force or stale or built_for != cpu:
         subprocess.check_call(["make", "-C", _HERE, "-B", "libqc_oracle.so"], stdout=subprocess.DEVNULL)
+        with open(stamp, "w") as f:
+            f.write(cpu)
     return so
 
 

@@ -68,8 +68,10 @@ QCOH_SYMBOLS = ("qcoh_version", "qcoh_device_count", "qcoh_set_device", "qcoh_ho
                 "qcoh_device_alloc", "qcoh_device_free", "qcoh_memcpy_h2d", "qcoh_memcpy_d2h",
                 "qcoh_device_synchronize", "qcoh_timer_start", "qcoh_timer_stop", "qcoh_flush_l2",
                 "qcoh_booster_parse", "qcoh_booster_get_info", "qcoh_booster_get_flat", "qcoh_booster_get_duo",
+                "qcoh_booster_get_duo_info",
                 "qcoh_dmatrix_create_device", "qcoh_dmatrix_device_ptr", "qcoh_dmatrix_upload", "qcoh_dmatrix_seal",
-                "qcoh_booster_predict_device", "qcoh_set_param", "qcoh_launch_count", "qcoh_oh_create",
+                "qcoh_booster_predict_device", "qcoh_set_param", "qcoh_launch_count", "qcoh_kernel_launches",
+                "qcoh_last_predict_kernel", "qcoh_dmatrix_tiles_ptr", "qcoh_oh_invalidate_sza", "qcoh_oh_create",
                 "qcoh_oh_run1", "qcoh_oh_free", "qcoh_oh_get_diag", "qcoh_predict_OH_with_XGB", "qcoh_predict_OH_reset",
                 "qcoh_predict_OH_reload_on_file_change", "qcoh_oh_set_booster", "qcoh_oh_get_booster",
                 "qcoh_expand_template", "qcoh_model_cache_get", "qcoh_model_cache_size", "qcoh_model_cache_clear",
@@ -91,6 +93,11 @@ def lib():
         L.XGBGetLastError.restype = C.c_char_p
         L.qcoh_version.restype = C.c_char_p
         L.qcoh_launch_count.restype = C.c_uint64
+        L.qcoh_kernel_launches.restype = C.c_uint64
+        L.qcoh_kernel_launches.argtypes = [C.c_char_p]
+        L.qcoh_last_predict_kernel.restype = C.c_char_p
+        L.qcoh_dmatrix_tiles_ptr.argtypes = [vp, C.POINTER(vp), C.POINTER(u64)]
+        L.qcoh_oh_invalidate_sza.argtypes = [vp]
         L.XGBoosterCreate.argtypes = [vp, u64, C.POINTER(vp)]
         L.XGBoosterFree.argtypes = [vp]
         L.XGBoosterLoadModel.argtypes = [vp, C.c_char_p]
@@ -116,6 +123,7 @@ def lib():
                                             C.POINTER(C.POINTER(C.c_int32)), C.POINTER(C.POINTER(C.c_int32))]  # fmt: skip
         L.qcoh_booster_get_duo.argtypes = [vp, C.POINTER(C.POINTER(C.c_uint32)), C.POINTER(C.POINTER(C.c_uint32)),
                                            C.POINTER(C.POINTER(C.c_uint32)), C.POINTER(C.c_int64)]  # fmt: skip
+        L.qcoh_booster_get_duo_info.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]
         L.qcoh_dmatrix_create_device.argtypes = [u64, u64, C.c_float, C.POINTER(vp)]
         L.qcoh_dmatrix_device_ptr.argtypes = [vp, C.POINTER(vp)]
         L.qcoh_dmatrix_upload.argtypes = [vp, vp, u64, u64]
@@ -166,6 +174,15 @@ def set_param(name: str, value) -> None:
 
 def launch_count() -> int:
     return int(lib().qcoh_launch_count())
+
+
+def kernel_launches(family: str) -> int:
+    """Launches of one kernel family since load ("duo", "duo_missing", "duo_leaf", "nodes8", ...)."""
+    return int(lib().qcoh_kernel_launches(family.encode()))
+
+
+def last_predict_kernel() -> str:
+    return lib().qcoh_last_predict_kernel().decode()
 
 
 def partition_columns(ncol_global: int, nranks: int, rank: int):
@@ -364,6 +381,12 @@ class Booster:
         nt = self.info().num_trees
         rec = np.ctypeslib.as_array(pr, (n.value * 4,)).reshape(n.value, 4).copy()
         return rec, np.ctypeslib.as_array(ps, (nt,)).copy(), np.ctypeslib.as_array(pt, (nt * 32,)).reshape(nt, 16, 2).copy()
+
+    def duo_info(self):
+        """(blk_shift, has_default_bits) of the two-level records."""
+        sh, dl = C.c_int(), C.c_int()
+        check(lib().qcoh_booster_get_duo_info(self.handle, C.byref(sh), C.byref(dl)))
+        return sh.value, bool(dl.value)
 
     def predict(self, dmat: DMatrix, option_mask=0, ntree_limit=0, training=0) -> np.ndarray:
         """XGBoosterPredict_f(handle, dmat, option_mask, ntree_limit, training, length, prediction).

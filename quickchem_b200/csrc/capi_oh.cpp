@@ -13,6 +13,8 @@ int julian_day(int nymd) {
   static const int days[12] = {31, 28, 31, 30, 31, 30, 31, 31, 30, 31, 30, 31};
   const int ny = nymd / 10000, mm = (nymd % 10000) / 100;
   int ds = nymd % 100;
+  if (nymd < 0 || mm < 1 || mm > 12 || ds < 1 || ds > ((mm == 2 && is_leap(ny)) ? 29 : days[mm - 1]))
+    throw Error("qcoh_oh_run1: nymd = " + std::to_string(nymd) + " is not a yyyymmdd date");
   for (int m = 1; m < mm; ++m) ds += (m == 2 && is_leap(ny)) ? 29 : days[m - 1];
   return ds;
 }
@@ -59,19 +61,50 @@ struct Oh {
   // resident copies of host-provided inputs, one slot per input field
   static constexpr int kNumIn = 13 + 7 + 11 + 5 + 1 + 1;
   DevBuf<float> in[kNumIn];
-  DevBuf<float> PL_MOD, NDWET, sums[6], OH_ML, OH, OH_boost, X, pred, sza, lat_deg, so3, loss_ch4, loss_co;
+  DevBuf<float> PL_MOD, NDWET, sums[6], aod, pl_bst, OH_ML, OH, OH_boost, X, pred, sza, lat_deg, so3, loss_ch4, loss_co;
+  DevBuf<uint32_t> Xt;
   DevBuf<int> ctl;
   DevBuf<double> diag;
-  PinBuf<float> h_sza, h_lat, h_lon;
+  PinBuf<float> h_sza, h_lat, h_lon, h_probe;
+  // noon-SZA cache key: day of year, the grid's size and addresses, and a hash of a strided sample of LATS / LONS
+  // (a host that re-uses its buffers for another grid gets a new SZA; qcoh_oh_invalidate_sza forces one)
   int sza_jday = -1;
+  size_t sza_n = 0;
   const float *sza_lat_key = nullptr, *sza_lon_key = nullptr;
+  uint64_t sza_hash = 0;
   bool oh_ml_valid = false;
+  ~Oh() {
+    if (booster) --booster->oh_refs;
+  }
 };
+
+constexpr int kProbe = 2048;
+// FNV-1a over a strided sample of both coordinate arrays (host or device memory)
+uint64_t grid_probe_hash(Oh *o, const float *lat, const float *lon, size_t n) {
+  const size_t stride = std::max<size_t>(1, n / kProbe), cnt = std::min<size_t>(n, (n + stride - 1) / stride);
+  float *h = o->h_probe.need(2 * (size_t)kProbe + 2);
+  CU(cudaMemcpy2DAsync(h, sizeof(float), lat, stride * sizeof(float), sizeof(float), cnt, cudaMemcpyDefault, g.stream));
+  CU(cudaMemcpy2DAsync(h + cnt, sizeof(float), lon, stride * sizeof(float), sizeof(float), cnt, cudaMemcpyDefault, g.stream));
+  CU(cudaMemcpyAsync(h + 2 * cnt, lat + (n - 1), sizeof(float), cudaMemcpyDefault, g.stream));
+  CU(cudaMemcpyAsync(h + 2 * cnt + 1, lon + (n - 1), sizeof(float), cudaMemcpyDefault, g.stream));
+  CU(cudaStreamSynchronize(g.stream));
+  uint64_t x = 1469598103934665603ull;
+  const unsigned char *b = (const unsigned char *)h;
+  for (size_t i = 0; i < (2 * cnt + 2) * sizeof(float); ++i) x = (x ^ b[i]) * 1099511628211ull;
+  return x;
+}
 
 Oh *O(qcoh_oh_handle h) {
   Oh *o = (Oh *)h;
-  if (!o || o->magic != kOhMagic) throw Error("Invalid OH handle");
+  if (!o || !is_live(h) || o->magic != kOhMagic) throw Error("Invalid OH handle");
   return o;
+}
+
+void bind_booster(Oh *o, Booster *b) {
+  if (o->booster == b) return;
+  if (o->booster) --o->booster->oh_refs;
+  o->booster = b;
+  ++b->oh_refs;
 }
 
 // host pointer -> resident device copy; device pointer -> used in place
@@ -103,10 +136,12 @@ int qcoh_oh_create(BoosterHandle booster, const qcoh_oh_config *cfg, qcoh_oh_han
   ensure_device();
   upload(b);
   std::unique_ptr<Oh> o(new Oh());
-  o->booster = b, o->cfg = *cfg;
+  bind_booster(o.get(), b);
+  o->cfg = *cfg;
   const size_t n3 = (size_t)cfg->ncol * cfg->km;
   o->OH_ML.need(n3);
   CU(cudaMemsetAsync(o->OH_ML.p, 0, n3 * 4, g.stream));
+  g_live_handles.insert(o.get());
   *out = o.release();
   API_END
 }
@@ -120,7 +155,7 @@ int qcoh_oh_set_booster(qcoh_oh_handle h, BoosterHandle booster) {
     throw Error("OH_GridComp packs exactly 27 features (OH_GridCompMod.F90:228); the booster has " + std::to_string(b->host.num_feature));
   ensure_device();
   upload(b);
-  o->booster = b;
+  bind_booster(o, b);
   API_END
 }
 
@@ -143,8 +178,10 @@ int qcoh_oh_get_diag(qcoh_oh_handle h, const char *name, float *out) {
   static const char *sum_names[6] = {"TAUCLWDN", "TAUCLIDN", "TAUCLIUP", "TAUCLWUP", "AODUP", "AODDN"};
   for (int i = 0; i < 6; ++i)
     if (s == sum_names[i]) src = o->sums[i].p;
-  if (s == "PL") src = o->PL_MOD.p;
-  if (s == "NDWET") src = o->NDWET.p;
+  if (s == "PL") src = o->pl_bst.p;      // bb%PL = PL_BST, from the PLE handed to boost (:1488, :1666)
+  if (s == "AOD") src = o->aod.p;        // :1690
+  if (s == "PL_MOD") src = o->PL_MOD.p;  // current step (not a reference export)
+  if (s == "NDWET") src = o->NDWET.p;    // NDWET_MOD of the CURRENT step, as DIAG_NDWET (:1598-1599)
   if (s == "OH_boost") src = o->OH_ML.p;
   if (s == "LAT") src = o->lat_deg.p, n = n2;
   if (s == "SZA") src = o->sza.p, n = n2;
@@ -158,8 +195,16 @@ int qcoh_oh_get_diag(qcoh_oh_handle h, const char *name, float *out) {
 int qcoh_oh_free(qcoh_oh_handle h) {
   API_BEGIN
   Oh *o = O(h);
+  if (g.ready) CU(cudaStreamSynchronize(g.stream));
   o->magic = 0;
+  g_live_handles.erase(o);
   delete o;
+  API_END
+}
+
+int qcoh_oh_invalidate_sza(qcoh_oh_handle h) {
+  API_BEGIN
+  O(h)->sza_jday = -1;
   API_END
 }
 
@@ -218,14 +263,15 @@ int qcoh_oh_run1(qcoh_oh_handle h, const qcoh_run1_in *in, qcoh_run1_out *out) {
     if (!in->LONS) throw Error("qcoh_oh_run1: input field LONS is NULL");
     // noon SZA (host libm, cached per day and grid)
     const int jday = julian_day(in->nymd);
-    if (jday != o->sza_jday || in->LATS != o->sza_lat_key || in->LONS != o->sza_lon_key) {
+    const uint64_t probe = grid_probe_hash(o, in->LATS, in->LONS, n2);
+    if (jday != o->sza_jday || in->LATS != o->sza_lat_key || in->LONS != o->sza_lon_key || n2 != o->sza_n || probe != o->sza_hash) {
       float *hl = o->h_lat.need(n2), *hn = o->h_lon.need(n2), *hs = o->h_sza.need(n2);
       CU(cudaMemcpyAsync(hl, in->LATS, n2 * 4, cudaMemcpyDefault, g.stream));
       CU(cudaMemcpyAsync(hn, in->LONS, n2 * 4, cudaMemcpyDefault, g.stream));
       CU(cudaStreamSynchronize(g.stream));
       noon_sza(jday, hl, hn, nc, c.mapl_radians_to_degrees, c.mapl_degrees_to_radians, hs);
       CU(cudaMemcpyAsync(o->sza.need(n2), hs, n2 * 4, cudaMemcpyHostToDevice, g.stream));
-      o->sza_jday = jday, o->sza_lat_key = in->LATS, o->sza_lon_key = in->LONS;
+      o->sza_jday = jday, o->sza_lat_key = in->LATS, o->sza_lon_key = in->LONS, o->sza_n = n2, o->sza_hash = probe;
     }
     r.SZA = o->sza.p;
   }
@@ -251,12 +297,14 @@ int qcoh_oh_run1(qcoh_oh_handle h, const qcoh_run1_in *in, qcoh_run1_out *out) {
     const uint64_t npred = (uint64_t)nc * ksub;
     for (int i = 0; i < 6; ++i) r.sums[i] = o->sums[i].need(n3);
     r.lat_deg = o->lat_deg.need(n2), r.so3 = o->so3.need(n2);
+    r.aod = o->aod.need(n3), r.pl_bst = o->pl_bst.need(n3);
     CU(launch_oh_sums(r, g.stream));
-    B(o->booster);  // a freed booster fails here rather than in a kernel
+    B(o->booster);  // the handle holds a reference (XGBoosterFree refuses while it does); checked all the same
     upload(o->booster);
-    sync_const_top(o->booster, true);  // clean tiles walk the two-level records when the booster qualifies
+    sync_const_top(o->booster, true);  // tiles walk the two-level records when the booster qualifies
     CU(cudaMemsetAsync(r.OH_ML, 0, n3 * 4, g.stream));  // self%OH_ML = 0.0 (:1559)
-    if (npred && !out->X) {
+    const bool too_many_trees = o->booster->dev.ntree > kConstTreesMax;  // chunked launches need the matrix form
+    if (npred && !out->X && !too_many_trees) {
       // fused: pack (:303-345) + create (:347) + predict (:356) + 10**x (:369) * OHscale (:1569) in one
       // kernel reading the SoA fields; the [N x 27] matrix is never formed
       SoaArgs a;
@@ -282,17 +330,21 @@ int qcoh_oh_run1(qcoh_oh_handle h, const qcoh_run1_in *in, qcoh_run1_out *out) {
       CU(cudaMemcpyAsync(&flags, r.ctl + 2, sizeof(int), cudaMemcpyDeviceToHost, g.stream));
       CU(cudaStreamSynchronize(g.stream));
       if ((flags & 2) && !std::isinf(c.missing)) throw Error("Check failed: valid: Input data contains `inf` or `nan`");
+      // XGDMatrixCreateFromMat (:347): scan + key tiles
+      uint32_t *Xt = o->Xt.need(tile_words(npred, 27));
+      CU(launch_seal_tiles(X, npred, 27, c.missing, Xt, r.ctl + 3, g.stream));
       PredictArgs a;
-      a.X = X, a.nrow = npred, a.ncol = 27, a.missing = c.missing, a.has_missing = flags & 1, a.pred_leaf = 0;
-      a.ntree_used = o->booster->dev.ntree, a.exp10 = 1, a.scale = c.ohscale;
+      a.Xt = Xt, a.nrow = npred, a.ncol = 27, a.has_missing = flags & 1, a.pred_leaf = 0;
+      a.tree_begin = 0, a.tree_end = o->booster->dev.ntree, a.out_stride = a.tree_end;
+      a.exp10 = 1, a.scale = c.ohscale;
       a.out = r.OH_ML + (size_t)(k1 - 1) * nc;
-      CU(launch_predict(o->booster->dev, a, g.tun, g.stream));
+      launch_predict_chunked(o->booster, a, true, g.stream);
       if (out->pred) {
         a.exp10 = 0, a.scale = 1.f, a.out = o->pred.need(npred);
-        CU(launch_predict(o->booster->dev, a, g.tun, g.stream));
+        launch_predict_chunked(o->booster, a, true, g.stream);
         deliver(out->pred, a.out, npred);
       }
-      deliver(out->X, X, npred * 27);
+      if (out->X) deliver(out->X, X, npred * 27);
     }
     o->oh_ml_valid = true;
   }

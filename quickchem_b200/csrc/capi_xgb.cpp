@@ -3,6 +3,12 @@
 // Everything numerical is a kernel launch (kernels.cu); there is no CPU compute path.
 #include "context.hpp"
 
+#include <condition_variable>
+#include <mutex>
+#ifdef __linux__
+#include <sched.h>
+#endif
+
 using namespace qcoh;
 
 namespace qcoh {
@@ -44,6 +50,8 @@ void upload(Booster *b) {
   b->dev.max_depth = f.max_depth;
   b->dev.num_nodes = f.num_nodes();
   b->dev.base_score = b->host.base_score;
+  b->dev.sum_depth = 0;
+  for (int32_t d : f.tree_depth) b->dev.sum_depth += d;
   if (b->dev.tex) cudaDestroyTextureObject(b->dev.tex);
   b->dev.tex = 0;
   if (nn > 0 && nn < ((size_t)1 << 27)) {
@@ -60,7 +68,7 @@ void upload(Booster *b) {
   }
   // two-level records, when every tree qualifies
   if (b->dev.tex4) cudaDestroyTextureObject(b->dev.tex4);
-  b->dev.tex4 = 0, b->dev.recs = nullptr, b->dev.duo_ready = 0;
+  b->dev.tex4 = 0, b->dev.recs = nullptr, b->dev.duo_ready = 0, b->dev.duo_has_dl = 0, b->dev.duo_blk_mul = 0;
   if (b->duo.ok && b->duo.num_slots() > 0 && b->duo.num_slots() < ((int64_t)1 << 27)) {
     const size_t ns = (size_t)b->duo.num_slots();
     CU(cudaMemcpy(b->d_recs.need(ns), b->duo.rec.data(), ns * 16, cudaMemcpyHostToDevice));
@@ -75,16 +83,20 @@ void upload(Booster *b) {
     td.readMode = cudaReadModeElementType;
     CU(cudaCreateTextureObject(&b->dev.tex4, &rd, &td, nullptr));
     b->dev.recs = b->d_recs.p;
+    b->dev.duo_has_dl = b->duo.has_default_bits ? 1 : 0;
+    b->dev.duo_blk_mul = 1u << (32 - b->duo.blk_shift);
   }
   b->uploaded = true;
 }
 
-// The constant-memory table of tree tops belongs to one booster at a time, in one of two layouts: the first
-// levels of the depth-ordered nodes (walk_group), or the complete heap-ordered tops of the two-level records
-// (walk_group_duo).  allow_duo: the caller's next launches are clean-matrix sums, which the two-level kernel
-// serves when the booster qualifies; anything else then runs without a constant table (still correct).
+// The constant-memory tables of tree tops are one per process (one __constant__ bank per loaded module): they
+// hold one range of <= kConstTreesMax trees of one booster at a time, in one of two layouts — the first levels
+// of the depth-ordered nodes (walk_group), or the complete heap-ordered tops of the two-level records
+// (walk_group_duo).  The owner tag below is therefore process-wide by construction; everything else a launch
+// needs travels in the booster's DeviceForest.  allow_duo = false forces the 8-byte-node layout.
 static uint64_t g_const_top_owner = 0;
 static int g_const_top_levels = 0;  // kConstDuo = two-level layout
+static int g_const_tree0 = 0, g_const_ntree = 0;
 constexpr int kConstDuo = -1;
 bool duo_wanted(const Booster *b) {
   if (b->dev.recs == nullptr || b->dev.tex == 0 || g.tun.duo == 0) return false;
@@ -92,40 +104,73 @@ bool duo_wanted(const Booster *b) {
   // default: on, unless an experiment knob of the 8-byte-node kernel is set
   return kDuoDefault && g.tun.variant == 0 && g.tun.park != 0 && g.tun.top_levels < 0 && g.tun.ilp == 0 && g.tun.minb == 0;
 }
-void sync_const_top(Booster *b, bool allow_duo) {
-  b->dev.const_top_levels = 0, b->dev.duo_ready = 0;
+void sync_const_top(Booster *b, bool allow_duo, int tree0, int ntree) {
+  b->dev.const_top_levels = 0, b->dev.duo_ready = 0, b->dev.const_tree0 = tree0, b->dev.const_ntree = 0;
+  // hold as many trees from tree0 on as fit, so that calls with different ntree_limit do not thrash the table
+  const int hold = std::min(b->dev.ntree - tree0, kConstTreesMax);
+  if (ntree < 0) ntree = hold;
+  if (ntree <= 0 || ntree > hold) return;
+  auto holds = [&](int layout) {
+    return g_const_top_owner == b->version && g_const_top_levels == layout && g_const_tree0 == tree0 && g_const_ntree >= ntree;
+  };
   if (allow_duo && duo_wanted(b)) {
-    if (g_const_top_owner != b->version || g_const_top_levels != kConstDuo) {
-      if (upload_const_duo(b->duo.top_xy.data(), b->duo.tree_slot.data(), b->dev.ntree, g.stream) == cudaSuccess) {
-        g_const_top_owner = b->version, g_const_top_levels = kConstDuo;
+    if (!holds(kConstDuo)) {
+      g_const_top_owner = 0;
+      if (upload_const_duo(b->duo.top_xy.data() + (size_t)tree0 * (2u << kDuoTop), b->duo.tree_slot.data() + tree0, hold, g.stream) ==
+          cudaSuccess) {
+        g_const_top_owner = b->version, g_const_top_levels = kConstDuo, g_const_tree0 = tree0, g_const_ntree = hold;
       } else {
         (void)cudaGetLastError();
-        g_const_top_owner = 0;
       }
     }
-    if (g_const_top_owner == b->version && g_const_top_levels == kConstDuo) {
-      b->dev.duo_ready = 1;
+    if (holds(kConstDuo)) {
+      b->dev.duo_ready = 1, b->dev.const_ntree = g_const_ntree;
       return;
     }
   }
   const int want = g.tun.top_levels < 0 ? 4 : g.tun.top_levels;
   if (want <= 0) return;
-  if (g_const_top_owner != b->version || g_const_top_levels != want) {
+  if (!holds(want)) {
     g_const_top_owner = 0;
-    if (upload_const_top(b->dev_nodes_host.data(), b->flat.tree_offset.data(), b->dev.ntree, want, g.stream) != cudaSuccess) {
+    if (upload_const_top(b->dev_nodes_host.data(), b->flat.tree_offset.data() + tree0, hold, want, g.stream) != cudaSuccess) {
       (void)cudaGetLastError();
       return;  // does not fit: the kernel runs without the table
     }
-    g_const_top_owner = b->version, g_const_top_levels = want;
+    g_const_top_owner = b->version, g_const_top_levels = want, g_const_tree0 = tree0, g_const_ntree = hold;
   }
-  b->dev.const_top_levels = want;
+  b->dev.const_top_levels = want, b->dev.const_ntree = g_const_ntree;
+}
+
+// One prediction = one launch per range of kConstTreesMax trees: the tables are re-filled between the launches
+// (stream-ordered) and the float32 partial sum travels through `out`, so the sum order — tree 0, 1, 2, ... — and
+// with it every bit of the result is the same as in a single launch.
+void launch_predict_chunked(Booster *b, PredictArgs a, bool allow_duo, cudaStream_t s) {
+  const int t_end = a.tree_end;
+  if (a.nrow == 0) return;
+  if (t_end <= 0) {  // a booster without trees predicts its base score
+    if (!a.pred_leaf) {
+      float v = b->host.base_score;
+      if (a.exp10) v = (float)exp10((double)v) * a.scale;
+      CU(launch_fill(a.out, a.nrow, v, s));
+    }
+    return;
+  }
+  for (int t0 = 0; t0 < t_end; t0 += kConstTreesMax) {
+    const int n = std::min(kConstTreesMax, t_end - t0);
+    sync_const_top(b, allow_duo, t0, n);
+    PredictArgs c = a;
+    c.tree_begin = t0, c.tree_end = t0 + n;
+    c.first = t0 == 0, c.last = t0 + n == t_end;
+    CU(launch_predict(b->dev, c, g.tun, s));
+  }
 }
 
 static void seal(DMatrix *d) {
   ensure_device();
   int *fl = d->flags.need(1);
   CU(cudaMemsetAsync(fl, 0, sizeof(int), g.stream));
-  CU(launch_scan_matrix(d->X.p, d->nrow * d->ncol, d->missing, fl, g.stream));
+  if (g_spare_Xt.cap >= tile_words(d->nrow, d->ncol) && g_spare_Xt.p && !d->Xt.p) d->Xt.swap(g_spare_Xt);
+  CU(launch_seal_tiles(d->X.p, d->nrow, (int)d->ncol, d->missing, d->Xt.need(tile_words(d->nrow, d->ncol)), fl, g.stream));
   CU(cudaMemcpyAsync(&d->hflags, fl, sizeof(int), cudaMemcpyDeviceToHost, g.stream));
   CU(cudaStreamSynchronize(g.stream));
   d->sealed = true;
@@ -146,15 +191,14 @@ static void predict_into(Booster *b, DMatrix *d, int option_mask, unsigned ntree
     throw Error("Check failed: Number of columns does not match number of features in booster. Columns: " +
                 std::to_string(d->ncol) + " Features: " + std::to_string(b->host.num_feature));
   PredictArgs a;
-  a.X = d->X.p, a.nrow = d->nrow, a.ncol = (int32_t)d->ncol, a.missing = d->missing;
+  a.Xt = d->Xt.p, a.nrow = d->nrow, a.ncol = (int32_t)d->ncol;
   a.has_missing = ((d->hflags & 1) || d->ncol < b->host.num_feature) ? 1 : 0;
   a.pred_leaf = (option_mask & 2) ? 1 : 0;
-  sync_const_top(b, !a.has_missing && !a.pred_leaf);
-  a.ntree_used = (int32_t)trees_used(b, ntree_limit);
+  a.tree_begin = 0, a.tree_end = (int32_t)trees_used(b, ntree_limit), a.out_stride = a.tree_end;
   a.exp10 = epi ? epi->exp10 : 0;
   a.scale = epi ? epi->scale : 1.f;
   a.out = out_dev;
-  CU(launch_predict(b->dev, a, g.tun, g.stream));
+  launch_predict_chunked(b, a, true, g.stream);
 }
 
 static cudaEvent_t chunk_event(size_t i) {
@@ -182,26 +226,87 @@ static bool is_pinned_host(const void *p) {
   return a.type == cudaMemoryTypeHost;
 }
 
-// multi-threaded memcpy (pageable host -> pinned staging)
-static void parallel_memcpy(void *dst, const void *src, size_t bytes) {
-  unsigned nt = std::thread::hardware_concurrency();
-  if (nt == 0) nt = 1;
-  if (nt > 16) nt = 16;
-  if (bytes < ((size_t)8 << 20)) nt = 1;
-  if (nt == 1) {
-    memcpy(dst, src, bytes);
-    return;
+// Multi-threaded memcpy (pageable host -> pinned staging) on a persistent pool: a Fortran ALLOCATE gives pageable
+// memory (xx_carr, OH_GridCompMod.F90:306), and one core's memcpy (~10 GB/s) is far below PCIe 5 x16.  The
+// workers are created once and parked on a condition variable; spawning threads per chunk cost more than the copy
+// of a small chunk.  Threads: the cores this process may use divided by the ranks sharing the node.
+class CopyPool {
+ public:
+  static CopyPool &get() {
+    static CopyPool p;
+    return p;
   }
-  std::vector<std::thread> th;
-  const size_t per = (bytes / nt + 4095) / 4096 * 4096;
-  for (unsigned t = 0; t < nt; ++t) {
-    const size_t o = (size_t)t * per;
-    if (o >= bytes) break;
-    const size_t n = std::min(per, bytes - o);
-    th.emplace_back([=] { memcpy((char *)dst + o, (const char *)src + o, n); });
+  void copy(void *dst, const void *src, size_t bytes) {
+    const unsigned nt = (unsigned)workers_.size() + 1;
+    if (nt == 1 || bytes < ((size_t)4 << 20)) {
+      memcpy(dst, src, bytes);
+      return;
+    }
+    const size_t per = (bytes / nt + 4095) / 4096 * 4096;
+    {
+      std::lock_guard<std::mutex> lk(m_);
+      dst_ = (char *)dst, src_ = (const char *)src, bytes_ = bytes, per_ = per;
+      pending_ = (unsigned)workers_.size();
+      ++generation_;
+    }
+    cv_.notify_all();
+    part(nt - 1);  // the caller copies the last part
+    std::unique_lock<std::mutex> lk(m_);
+    done_.wait(lk, [&] { return pending_ == 0; });
   }
-  for (auto &t : th) t.join();
-}
+  unsigned threads() const { return (unsigned)workers_.size() + 1; }
+
+ private:
+  CopyPool() {
+    unsigned cores = std::thread::hardware_concurrency();
+#ifdef __linux__
+    cpu_set_t set;
+    if (sched_getaffinity(0, sizeof set, &set) == 0) cores = (unsigned)CPU_COUNT(&set);
+#endif
+    if (cores == 0) cores = 1;
+    unsigned share = 1;
+    if (const char *lw = getenv("LOCAL_WORLD_SIZE")) share = (unsigned)std::max(1, atoi(lw));
+    unsigned nt = std::max(1u, std::min(32u, cores / share));
+    if (const char *e = getenv("QCOH_COPY_THREADS")) nt = (unsigned)std::max(1, atoi(e));
+    for (unsigned t = 0; t + 1 < nt; ++t) workers_.emplace_back([this, t] { run(t); });
+  }
+  ~CopyPool() {
+    {
+      std::lock_guard<std::mutex> lk(m_);
+      stop_ = true;
+    }
+    cv_.notify_all();
+    for (auto &w : workers_) w.join();
+  }
+  void part(unsigned t) {
+    const size_t o = (size_t)t * per_;
+    if (o < bytes_) memcpy(dst_ + o, src_ + o, std::min(per_, bytes_ - o));
+  }
+  void run(unsigned t) {
+    uint64_t seen = 0;
+    for (;;) {
+      {
+        std::unique_lock<std::mutex> lk(m_);
+        cv_.wait(lk, [&] { return stop_ || generation_ != seen; });
+        if (stop_) return;
+        seen = generation_;
+      }
+      part(t);
+      std::lock_guard<std::mutex> lk(m_);
+      if (--pending_ == 0) done_.notify_one();
+    }
+  }
+  std::vector<std::thread> workers_;
+  std::mutex m_;
+  std::condition_variable cv_, done_;
+  char *dst_ = nullptr;
+  const char *src_ = nullptr;
+  size_t bytes_ = 0, per_ = 0;
+  unsigned pending_ = 0;
+  uint64_t generation_ = 0;
+  bool stop_ = false;
+};
+static void parallel_memcpy(void *dst, const void *src, size_t bytes) { CopyPool::get().copy(dst, src, bytes); }
 
 constexpr int kStageSlots = 3;
 static PinBuf<float> g_stage[kStageSlots];
@@ -216,7 +321,7 @@ static cudaEvent_t g_stage_free[kStageSlots] = {nullptr, nullptr, nullptr};
 // memory (what a Fortran ALLOCATE gives) is staged through a ring of pinned buffers by a threaded
 // memcpy so that the DMA engine never waits on the driver's own bounce buffer.  The caller's buffer
 // is fully consumed before this returns.
-//   copy_stream : H2D(c) -> scan(c) -> flag D2H(c)      g.stream : predict(c)      d2h_stream : result D2H(c)
+//   copy_stream : H2D(c) -> seal(c): scan + key tiles -> flag D2H(c)      g.stream : predict(c)      d2h_stream : result D2H(c)
 static void create_pipelined(DMatrix *d, const float *data, Booster *b) {
   const uint64_t nrow = d->nrow, ncol = d->ncol;
   const bool pinned = is_pinned_host(data);
@@ -224,11 +329,12 @@ static void create_pipelined(DMatrix *d, const float *data, Booster *b) {
   if (!pinned && cr > (1ull << 19)) cr = 1ull << 19;
   const size_t nchunk = (size_t)((nrow + cr - 1) / cr);
   float *X = d->X.p;
+  if (g_spare_Xt.cap >= tile_words(nrow, ncol) && g_spare_Xt.p && !d->Xt.p) d->Xt.swap(g_spare_Xt);
+  uint32_t *Xt = d->Xt.need(tile_words(nrow, ncol));
   const bool spec = b != nullptr;
   float *sdev = nullptr, *shost = nullptr;
   if (spec) {
     upload(b);
-    sync_const_top(b, ncol >= b->host.num_feature);  // chunks with missing entries then walk without the table
     if (g_spare_spec.cap >= nrow && g_spare_spec.p) d->spec_dev.swap(g_spare_spec);
     sdev = d->spec_dev.need(nrow);
     if (g_spare_pin.cap >= nrow && g_spare_pin.p) d->spec_host.swap(g_spare_pin);
@@ -256,7 +362,8 @@ static void create_pipelined(DMatrix *d, const float *data, Booster *b) {
     } else {
       CU(cudaMemcpyAsync(X + r0 * ncol, src, bytes, cudaMemcpyHostToDevice, g.copy_stream));
     }
-    CU(launch_scan_matrix(X + r0 * ncol, nr * ncol, d->missing, fl + c, g.copy_stream));
+    // chunks start on tile boundaries (chunk_rows is a multiple of 256)
+    CU(launch_seal_tiles(X + r0 * ncol, nr, (int)ncol, d->missing, Xt + r0 * ncol, fl + c, g.copy_stream));
     CU(cudaMemcpyAsync(hfl + c, fl + c, sizeof(int), cudaMemcpyDeviceToHost, g.copy_stream));
     CU(cudaEventRecord(chunk_event(2 * c), g.copy_stream));
   };
@@ -270,17 +377,17 @@ static void create_pipelined(DMatrix *d, const float *data, Booster *b) {
     }
     if (!spec) return;
     PredictArgs a;
-    a.X = X + r0 * ncol, a.nrow = nr, a.ncol = (int32_t)ncol, a.missing = d->missing;
+    a.Xt = Xt + r0 * ncol, a.nrow = nr, a.ncol = (int32_t)ncol;
     a.has_missing = ((hfl[c] & 1) || ncol < b->host.num_feature) ? 1 : 0;
-    a.ntree_used = (int32_t)b->host.trees.size();
+    a.tree_begin = 0, a.tree_end = (int32_t)b->host.trees.size(), a.out_stride = a.tree_end;
     a.out = sdev + r0;
-    CU(launch_predict(b->dev, a, g.tun, g.stream));
+    launch_predict_chunked(b, a, true, g.stream);
     CU(cudaEventRecord(chunk_event(2 * c + 1), g.stream));
     CU(cudaStreamWaitEvent(g.d2h_stream, chunk_event(2 * c + 1), 0));
     CU(cudaMemcpyAsync(shost + r0, sdev + r0, nr * sizeof(float), cudaMemcpyDeviceToHost, g.d2h_stream));
   };
-  // pinned source: every copy can be queued up front; pageable: stage one chunk ahead of the GPU
-  const size_t lookahead = pinned ? nchunk : 1;
+  // pinned source: every copy can be queued up front; pageable: stage two chunks ahead of the GPU (three slots)
+  const size_t lookahead = pinned ? nchunk : 2;
   for (size_t c = 0; c < nchunk + lookahead; ++c) {
     if (c < nchunk) issue(c);
     if (c >= lookahead && c - lookahead < nchunk) process(c - lookahead);
@@ -306,7 +413,9 @@ int XGBoosterCreate(const DMatrixHandle dmats[], bst_ulong len, BoosterHandle *o
   // dmats must not be dereferenced.  Cached matrices are a training concept; ignored for len > 0.
   (void)dmats, (void)len;
   if (!out) throw Error("XGBoosterCreate: out is NULL");
-  *out = new Booster();
+  Booster *b = new Booster();
+  g_live_handles.insert(b);
+  *out = b;
   API_END
 }
 
@@ -314,9 +423,12 @@ int XGBoosterFree(BoosterHandle handle) {
   API_BEGIN
   Booster *b = B(handle);
   if (b->cache_owned) throw Error("XGBoosterFree: this booster belongs to the model cache (qcoh_model_cache_clear frees it)");
+  if (b->oh_refs > 0)
+    throw Error("XGBoosterFree: " + std::to_string(b->oh_refs) + " fused-Run1 handle(s) still predict with this booster (qcoh_oh_free / qcoh_oh_set_booster first)");
   if (g_last_booster == b) g_last_booster = nullptr;
-  if (g.ready) CU(cudaStreamSynchronize(g.stream));
+  if (g.ready) drain();
   b->magic = 0;
+  g_live_handles.erase(b);
   delete b;
   API_END
 }
@@ -376,6 +488,7 @@ int XGDMatrixCreateFromMat(const float *data, bst_ulong nrow, bst_ulong ncol, fl
     }
     seal(d.get());
   }
+  g_live_handles.insert(d.get());
   *out = d.release();
   API_END
 }
@@ -383,11 +496,15 @@ int XGDMatrixCreateFromMat(const float *data, bst_ulong nrow, bst_ulong ncol, fl
 int XGDMatrixFree(DMatrixHandle handle) {
   API_BEGIN
   DMatrix *d = D(handle);
-  if (d->spec_ready) drain();  // pipelined work may still reference the buffers
+  // The freed buffers are pooled, not cudaFree'd (which would have synchronised): nothing may still be reading
+  // them — neither the pipelined create nor an asynchronous qcoh_booster_predict_device on the compute stream.
+  if (g.ready) drain();
   d->magic = 0;
   if (d->X.cap > g_spare_X.cap) d->X.swap(g_spare_X);
+  if (d->Xt.cap > g_spare_Xt.cap) d->Xt.swap(g_spare_Xt);
   if (d->spec_host.cap > g_spare_pin.cap) d->spec_host.swap(g_spare_pin);
   if (d->spec_dev.cap > g_spare_spec.cap) d->spec_dev.swap(g_spare_spec);
+  g_live_handles.erase(d);
   delete d;
   API_END
 }
@@ -670,6 +787,7 @@ int qcoh_set_param(const char *name, const char *value) {
   else if (n == "minb") g.tun.minb = v;
   else if (n == "duo") g.tun.duo = v;
   else if (n == "duo_mask") g.tun.duo_mask = v;
+  else if (n == "persist") g.tun.persist = v;
   else if (n == "speculate") g.speculate = v;
   else if (n == "chunk_rows") g.chunk_rows = v > 0 ? ((uint64_t)v + 255) / 256 * 256 : (1ull << 21);
   else throw Error("qcoh_set_param: unknown parameter '" + n + "'");
@@ -677,6 +795,8 @@ int qcoh_set_param(const char *name, const char *value) {
 }
 
 uint64_t qcoh_launch_count(void) { return launch_count(); }
+uint64_t qcoh_kernel_launches(const char *family) { return family ? kernel_launches(family) : 0; }
+const char *qcoh_last_predict_kernel(void) { return last_predict_kernel(); }
 
 int qcoh_booster_get_info(BoosterHandle handle, qcoh_booster_info *out) {
   API_BEGIN
@@ -717,12 +837,23 @@ int qcoh_booster_get_duo(BoosterHandle handle, const uint32_t **rec, const uint3
   API_END
 }
 
+int qcoh_booster_get_duo_info(BoosterHandle handle, int *blk_shift, int *has_default_bits) {
+  API_BEGIN
+  Booster *b = B(handle);
+  if (!b->loaded) throw Error("Booster has no model");
+  if (!b->duo.ok) throw Error("two-level records are not available for this booster: " + b->duo.why);
+  if (blk_shift) *blk_shift = b->duo.blk_shift;
+  if (has_default_bits) *has_default_bits = b->duo.has_default_bits ? 1 : 0;
+  API_END
+}
+
 int qcoh_dmatrix_create_device(bst_ulong nrow, bst_ulong ncol, float missing, DMatrixHandle *out) {
   API_BEGIN
   ensure_device();
   std::unique_ptr<DMatrix> d(new DMatrix());
   d->nrow = nrow, d->ncol = ncol, d->missing = missing;
   d->X.need((size_t)nrow * ncol);
+  g_live_handles.insert(d.get());
   *out = d.release();
   API_END
 }
@@ -744,6 +875,14 @@ int qcoh_dmatrix_upload(DMatrixHandle handle, const float *host_rows, bst_ulong 
 int qcoh_dmatrix_seal(DMatrixHandle handle) {
   API_BEGIN
   seal(D(handle));
+  API_END
+}
+int qcoh_dmatrix_tiles_ptr(DMatrixHandle handle, const uint32_t **out_dev, uint64_t *num_tiles) {
+  API_BEGIN
+  DMatrix *d = D(handle);
+  if (!d->sealed) seal(d);
+  if (out_dev) *out_dev = d->Xt.p;
+  if (num_tiles) *num_tiles = tile_count(d->nrow);
   API_END
 }
 

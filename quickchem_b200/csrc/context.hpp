@@ -13,6 +13,7 @@
 #include <stdexcept>
 #include <string>
 #include <thread>
+#include <unordered_set>
 #include <utility>
 #include <vector>
 
@@ -172,8 +173,13 @@ constexpr uint32_t kBoosterMagic = 0x51434253;  // 'QCBS'
 constexpr uint32_t kDMatrixMagic = 0x5143444d;  // 'QCDM'
 constexpr uint32_t kOhMagic = 0x51434f48;       // 'QCOH'
 
+// Live handles: a freed handle is recognised by its absence here, not by reading freed memory.
+inline std::unordered_set<const void *> g_live_handles;
+inline bool is_live(const void *h) { return h && g_live_handles.count(h) != 0; }
+
 struct Booster {
   uint32_t magic = kBoosterMagic;
+  int oh_refs = 0;       // fused-Run1 handles predicting with this booster: it cannot be freed while > 0
   uint64_t version = 0;  // changes with every (re)load
   bool loaded = false, uploaded = false;
   bool cache_owned = false;  // lives in the model cache (model_cache.cpp): not the caller's to free or reload
@@ -201,7 +207,8 @@ struct DMatrix {
   uint32_t magic = kDMatrixMagic;
   uint64_t nrow = 0, ncol = 0;
   float missing = NAN;
-  DevBuf<float> X;
+  DevBuf<float> X;       // row-major floats as handed in (XGDMatrixSaveBinary, qcoh_dmatrix_device_ptr)
+  DevBuf<uint32_t> Xt;   // the device form the kernels read: key tiles (kernels.hpp), built by seal
   DevBuf<int> flags;
   int hflags = 1;  // bit0 has-missing, bit1 has-inf; conservative until sealed
   bool sealed = false;
@@ -217,6 +224,7 @@ struct DMatrix {
 // reference creates and frees a same-sized DMatrix on every call (OH_GridCompMod.F90:347,377) and
 // cudaMalloc / cudaFree of multi-GB buffers would otherwise dominate the step.
 inline DevBuf<float> g_spare_X;
+inline DevBuf<uint32_t> g_spare_Xt;
 inline PinBuf<float> g_spare_pin;
 inline DevBuf<float> g_spare_spec;
 inline DevBuf<int> g_chunk_flags;
@@ -226,18 +234,20 @@ inline uint64_t g_version_counter = 0;
 
 inline Booster *B(BoosterHandle h) {
   Booster *b = (Booster *)h;
-  if (!b || b->magic != kBoosterMagic) throw Error("Invalid booster handle");
+  if (!b || !is_live(h) || b->magic != kBoosterMagic) throw Error("Invalid booster handle");
   return b;
 }
 inline DMatrix *D(DMatrixHandle h) {
   DMatrix *d = (DMatrix *)h;
-  if (!d || d->magic != kDMatrixMagic) throw Error("Invalid DMatrix handle");
+  if (!d || !is_live(h) || d->magic != kDMatrixMagic) throw Error("Invalid DMatrix handle");
   return d;
 }
 
 // capi_xgb.cpp
 void upload(Booster *b);
-// make the constant-memory table of tree tops hold this booster (see capi_xgb.cpp)
-void sync_const_top(Booster *b, bool allow_duo);
+// make the constant-memory tables of tree tops hold trees [tree0, tree0 + ntree) of this booster (see capi_xgb.cpp)
+void sync_const_top(Booster *b, bool allow_duo, int tree0 = 0, int ntree = -1);
+// one prediction = one launch per range of kConstTreesMax trees (capi_xgb.cpp)
+void launch_predict_chunked(Booster *b, PredictArgs a, bool allow_duo, cudaStream_t s);
 
 }  // namespace qcoh

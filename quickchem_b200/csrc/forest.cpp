@@ -782,12 +782,14 @@ FlatForest flatten(const HostForest &f) {
 }
 
 // ---- two-level records --------------------------------------------------------------------------
-DuoForest build_duo(const FlatForest &f, uint32_t num_feature) {
-  DuoForest out;
+static bool build_duo_with(const FlatForest &f, uint32_t num_feature, int blk_shift, DuoForest &out) {
+  const bool dlbits = blk_shift == 18;
+  out.blk_shift = blk_shift, out.has_default_bits = dlbits;
   const size_t ntree = f.tree_depth.size();
   auto X = [&](uint32_t n) { return f.nodes_xy[2 * (size_t)n]; };
   auto REL = [&](uint32_t n) { return f.nodes_xy[2 * (size_t)n + 1] & kMetaRelMask; };
   auto FEAT = [&](uint32_t n) { return f.nodes_xy[2 * (size_t)n + 1] >> kMetaFeatShift; };
+  auto DL = [&](uint32_t n) { return REL(n) != 0 && (f.nodes_xy[2 * (size_t)n + 1] & kMetaDefaultLeftBit) != 0; };
   auto thr_word = [&](uint32_t n) -> uint32_t {
     if (REL(n) == 0) return 0u;  // leaf child: compared against key 0 of the sentinel slot, never carries
     float thr;
@@ -807,7 +809,7 @@ DuoForest build_duo(const FlatForest &f, uint32_t num_feature) {
     for (uint32_t i = 1; i < kRow; ++i) {
       const uint32_t n = node[i];
       if (!pad[i] && REL(n) != 0) {
-        top[2 * i] = thr_word(n), top[2 * i + 1] = FEAT(n) << kMetaFeatShift;
+        top[2 * i] = thr_word(n), top[2 * i + 1] = (FEAT(n) << kMetaFeatShift) | (DL(n) ? kTopDefaultLeftBit : 0u);
         node[2 * i] = n + REL(n), node[2 * i + 1] = n + REL(n) + 1;
         pad[2 * i] = pad[2 * i + 1] = false;
       } else {  // a leaf above level kDuoTop, or padding below one: never right
@@ -831,9 +833,9 @@ DuoForest build_duo(const FlatForest &f, uint32_t num_feature) {
         } else {
           const uint32_t kids[2] = {n + REL(n), n + REL(n) + 1};
           const size_t blk = root_of.size() / 4;
-          if (blk >= (1u << (32 - kDuoBlkShift))) {
-            out.why = "tree " + std::to_string(t) + " needs more than 2^17 record blocks";
-            return out;
+          if (blk >= (1u << (32 - blk_shift))) {
+            out.why = "tree " + std::to_string(t) + " needs more than 2^" + std::to_string(32 - blk_shift) + " record blocks";
+            return false;
           }
           for (int c = 0; c < 2; ++c) {
             if (REL(kids[c]) == 0) {
@@ -844,18 +846,30 @@ DuoForest build_duo(const FlatForest &f, uint32_t num_feature) {
           }
           w[0] = thr_word(n), w[1] = thr_word(kids[0]), w[2] = thr_word(kids[1]);
           const uint32_t fl = REL(kids[0]) ? FEAT(kids[0]) : num_feature, fr = REL(kids[1]) ? FEAT(kids[1]) : num_feature;
-          w[3] = ((uint32_t)blk << kDuoBlkShift) | (fl << 10) | (fr << 5) | FEAT(n);
+          w[3] = ((uint32_t)blk << blk_shift) | (fl << 10) | (fr << 5) | FEAT(n);
+          if (dlbits) w[3] |= (DL(n) ? kDuoDlRoot : 0u) | (DL(kids[0]) ? kDuoDlLeft : 0u) | (DL(kids[1]) ? kDuoDlRight : 0u);
         }
       }
       out.rec.insert(out.rec.end(), w, w + 4);
     }
     if (out.rec.size() / 4 > 0x7FFFFFFFull) {
       out.why = "forest needs more than 2^31 records";
-      return out;
+      return false;
     }
   }
   out.ok = true;
-  return out;
+  return true;
+}
+
+DuoForest build_duo(const FlatForest &f, uint32_t num_feature) {
+  // with the three default-direction bits a tree may use 2^14 record blocks (1 MB of records); a bigger tree
+  // gets the 17-bit block pointer and no default bits (matrices with missing entries then walk the 8-byte nodes)
+  DuoForest out;
+  if (build_duo_with(f, num_feature, 18, out)) return out;
+  DuoForest wide;
+  if (build_duo_with(f, num_feature, 15, wide)) return wide;
+  wide.rec.clear(), wide.tree_slot.clear(), wide.top_xy.clear();
+  return wide;
 }
 
 }  // namespace qcoh

@@ -68,19 +68,25 @@ inline uint32_t neg_threshold_key(float thr) {
 }
 
 // Two-level records (DESIGN.md "Two levels per gather").  Levels 0..kDuoTop-1 of every tree are a COMPLETE
-// heap-ordered top (entry i = 1..15, children 2i and 2i+1; `top_xy` row of 16 {x, feat << 26} pairs per
-// tree, entry 0 unused) served from constant memory; a leaf above level kDuoTop is padded downwards with
+// heap-ordered top (entry i = 1..15, children 2i and 2i+1; `top_xy` row of 16 {x, feat << 26 | default_left} pairs
+// per tree, entry 0 unused) served from constant memory; a leaf above level kDuoTop is padded downwards with
 // never-right dummy nodes (x = 0, feat = num_feature).  Below, one 16-byte record holds a node at even depth
-// AND its two children, so one gather decides two levels.  {w0, w1, w2} = -key(threshold) of root / left / right (0 where that child is a leaf),
-// w3 = blk << 15 | feat(left) << 10 | feat(right) << 5 | feat(root); the four grandchild records sit
-// contiguously at tree-local slots blk*4 + 2*right1 + right2.  A leaf is a terminal record (w3 == 0,
-// w0 = value bits, w1 = XGBoost node id); a leaf CHILD has feature num_feature (whose key is 0: never
-// "right") and its terminal record sits at slot blk*4 + 2*side.
+// AND its two children, so one gather decides two levels.  {w0, w1, w2} = -key(threshold) of root / left / right
+// (0 where that child is a leaf), w3 = blk << blk_shift | [default-left bits] | feat(left) << 10 | feat(right) << 5 |
+// feat(root); the four grandchild records sit contiguously at tree-local slots blk*4 + 2*right1 + right2.  A leaf
+// is a terminal record (w3 == 0, w0 = value bits, w1 = XGBoost node id); a leaf CHILD has feature num_feature
+// (whose key is 0: never "right") and its terminal record sits at slot blk*4 + 2*side.
+//   blk_shift = 18: bits 17 / 16 / 15 of w3 are default_left of root / left / right (the missing-value direction,
+//                   xgboost RegTree::Node::DefaultLeft), leaving 14 bits for blk: every tree needs < 2^14 blocks
+//   blk_shift = 15: no default bits (a matrix with missing entries then walks the 8-byte nodes), 17-bit blk
 constexpr int kDuoTop = 4;
-constexpr uint32_t kDuoBlkShift = 15;
+constexpr uint32_t kDuoDlRoot = 1u << 17, kDuoDlLeft = 1u << 16, kDuoDlRight = 1u << 15;
+constexpr uint32_t kTopDefaultLeftBit = 1u;  // bit 0 of a top_xy y word
 struct DuoForest {
   bool ok = false;                    // false: some tree does not qualify (reason in `why`)
   std::string why;
+  int blk_shift = 18;
+  bool has_default_bits = true;       // blk_shift == 18
   std::vector<uint32_t> rec;          // 4 words per slot
   std::vector<uint32_t> tree_slot;    // [ntree] global slot of the tree's 16 level-kDuoTop records
   std::vector<uint32_t> top_xy;       // [ntree][16][2] heap-ordered tops for the constant-memory table

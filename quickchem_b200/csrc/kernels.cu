@@ -1,12 +1,15 @@
 // kernels.cu — hand-written sm_100a kernels of the OH hot path.
 //
-//   K2  predict_rows_kernel   tree-ensemble traversal, replaces libxgboost's CPUPredictor behind
-//                             XGBoosterPredict (reference call site OH_GridCompMod.F90:356) with the
-//                             export transform 10**x * OHscale (:369,:1569) fused as epilogue
-//   K2b predict_rows_duo_kernel   the same on two-level 16-byte records (one gather per two tree levels):
-//                             the default for sums over a matrix without missing entries
+//   K3  seal_tiles_kernel     the missing / inf scan of XGDMatrixCreateFromMat (OH_GridCompMod.F90:347) fused with
+//                             the conversion of the row-major float matrix into the DMatrix's device form:
+//                             feature-major tiles of order-preserving integer keys
+//   K2b predict_tiles_kernel  tree-ensemble traversal on two-level 16-byte records (one gather per two tree
+//                             levels), replaces libxgboost's CPUPredictor behind XGBoosterPredict (reference call
+//                             site :356) with the export transform 10**x * OHscale (:369,:1569) fused as epilogue;
+//                             sums / leaf indices, clean matrices / missing entries; tiles arrive by TMA, optionally
+//                             in a persistent double-buffered loop (shallow forests: the HBM-bound regime)
+//   K2  predict_tiles_nodes8_kernel   the same on the 8-byte depth-ordered nodes (boosters the records do not hold)
 //       predict_soa_kernel    K2 / K2b with the tile assembled straight from the Run1 SoA fields
-//   K3  scan_matrix_kernel    the missing / inf scan of XGDMatrixCreateFromMat (:347)
 //   K1  oh_state / oh_sums / oh_pack    Run1 feature assembly (:1240-1257, :1441-1488, :303-345)
 //   K5  oh_finalize           troposphere mask + unit conversion (:1579-1595)
 //   K4  oh_diag               build-defined mass-weighted mean OH / CH4 lifetime partial sums
@@ -18,6 +21,7 @@
 
 #include <cfloat>
 #include <cmath>
+#include <cstring>
 
 #include "forest.hpp"
 
@@ -28,29 +32,32 @@ uint64_t launch_count() { return g_launches; }
 
 #define QC_LAUNCHED() (++g_launches, cudaGetLastError())
 
-// =====================================================================================
-// K3 — matrix scan
-// =====================================================================================
-__global__ void __launch_bounds__(256) scan_matrix_kernel(const float *__restrict__ X, uint64_t n, float missing,
-                                                          int check_inf, int *flags) {
-  int f = 0;
-  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-    const float v = __ldg(X + i);
-    if (v != v || v == missing) f |= 1;
-    if (check_inf && isinf(v)) f |= 2;
-  }
-  f = __reduce_or_sync(0xffffffffu, f);
-  if ((threadIdx.x & 31) == 0 && f) atomicOr(flags, f);
+// launches per kernel family: what the parity tests assert ("this launch was served by the two-level kernel")
+namespace {
+struct FamilyCount {
+  char name[32];
+  uint64_t n;
+};
+FamilyCount g_family[24];
+int g_nfamily = 0;
+const char *g_last_predict = "";
+const char *count_family(const char *base, bool hm, bool pl) {
+  char name[32];
+  snprintf(name, sizeof name, "%s%s%s", base, hm ? "_missing" : "", pl ? "_leaf" : "");
+  for (int i = 0; i < g_nfamily; ++i)
+    if (!strcmp(g_family[i].name, name)) return ++g_family[i].n, g_family[i].name;
+  if (g_nfamily == 24) return "";
+  strcpy(g_family[g_nfamily].name, name);
+  g_family[g_nfamily].n = 1;
+  return g_family[g_nfamily++].name;
 }
-
-cudaError_t launch_scan_matrix(const float *X, uint64_t n, float missing, int *flags, cudaStream_t s) {
-  if (n == 0) return cudaSuccess;
-  int blocks = (int)((n + 255) / 256 < 148 * 16 ? (n + 255) / 256 : 148 * 16);
-  // xgboost src/data/data.cc: `!std::isinf(missing) && std::isinf(value)` invalidates the input
-  scan_matrix_kernel<<<blocks, 256, 0, s>>>(X, n, missing, std::isinf(missing) ? 0 : 1, flags);
-  return QC_LAUNCHED();
+}  // namespace
+uint64_t kernel_launches(const char *family) {
+  for (int i = 0; i < g_nfamily; ++i)
+    if (!strcmp(g_family[i].name, family)) return g_family[i].n;
+  return 0;
 }
+const char *last_predict_kernel() { return g_last_predict; }
 
 __global__ void fill_kernel(float *p, uint64_t n, float v) {
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
@@ -64,32 +71,30 @@ cudaError_t launch_fill(float *p, uint64_t n, float v, cudaStream_t s) {
 }
 
 // =====================================================================================
-// K2 — predict
+// Keys, tiles, constant tables
 // =====================================================================================
-// One thread = one row (grid cell).  The CTA's rows are staged in shared memory TRANSPOSED,
-// srow[f][tid]: whatever feature each lane asks for, lane L always hits bank L — the
-// data-dependent feature fetch is bank-conflict-free by construction.  The tile holds order-preserving
-// integer keys of the values (below); slot `nfeat` of every row holds key 0: leaves are encoded with
-// feat = nfeat and rel = 0, so the compare never says "right" there and the walk self-loops — no leaf
-// test inside the descent.  Missing entries (NaN or == missing) become key 0xFFFFFFFF while staging.
+// One thread = one row (grid cell).  A CTA's 256 rows sit in shared memory TRANSPOSED, skey[f][tid]:
+// whatever feature each lane asks for, lane L always hits bank L — the data-dependent feature fetch is
+// bank-conflict-free by construction.  The tile holds order-preserving integer keys of the values
+// (below); slot `nfeat` of every row holds key 0: leaves are encoded with feat = nfeat, so the compare
+// never says "right" there — no leaf test inside the descent.  Missing entries (NaN or == missing) are
+// key 0xFFFFFFFF.
 //
 // XGBoost semantics restated (xgboost 1.6.0 src/predictor/predict_fn.h GetNextNode,
 // src/predictor/cpu_predictor.cc PredictByAllTrees): missing -> default child, else
 // left + !(fvalue < split_cond); out = base_score, then += leaf value tree by tree in float32.
-#ifndef QC_BLOCK
-#define QC_BLOCK 256
-#endif
-constexpr int kBlock = QC_BLOCK;  // rows (= threads) per CTA
-constexpr int kStride = 256;      // feature stride of the transposed tile, in floats (1 KB: the PRMT address trick)
+constexpr int kBlock = kTileRows;  // rows (= threads) per CTA
+constexpr int kStride = kTileRows; // feature stride of the transposed tile, in keys (1 KB: the PRMT address trick)
+static_assert(kStride * 4 == 1024, "the address arithmetic of the walks assumes a 1 KB feature stride");
 
-// Order-preserving integer keys.  The tile and the device copy of the nodes do not hold floats but
-// key(v) = bits ^ (sign ? 0xFFFFFFFF : 0x80000000) of the value with -0.0 folded into +0.0, which is
-// monotone: a < b  <=>  key(a) < key(b) (unsigned) for all non-NaN floats, and key(-0) == key(+0) like
-// the float compare.  An internal node stores x = -key(threshold) (mod 2^32; key(thr) is never 0), so
+// Order-preserving integer keys: key(v) = bits ^ (sign ? 0xFFFFFFFF : 0x80000000) of the value with -0.0
+// folded into +0.0, which is monotone: a < b  <=>  key(a) < key(b) (unsigned) for all non-NaN floats, and
+// key(-0) == key(+0) like the float compare.  An internal node stores x = -key(threshold) (mod 2^32;
+// key(thr) is never 0), so
 //     !(v < thr)  <=>  key(thr) <= key(v)  <=>  x + key(v) >= 2^32
-// which is the carry of x + key(v): `add.cc` + `addc` fold the compare into the index update
-// (idx += rel + right) in two instructions and no predicate.  Missing is key 0xFFFFFFFF (above +inf).
-// The per-row slot `nfeat` that leaves point at holds key 0: nothing carries, the walk self-loops.
+// which is the carry of x + key(v): `add.cc` + `addc` fold the compare into the index update in two
+// instructions and no predicate.  Missing is key 0xFFFFFFFF (above +inf: it carries against every
+// threshold, and the walks that may see it test for it explicitly and take the default child).
 constexpr uint32_t kKeyMissing = 0xFFFFFFFFu;
 __device__ __forceinline__ uint32_t float_key(float v) {
   const uint32_t b = __float_as_uint(__fadd_rn(v, 0.0f));  // -0.0 + 0.0 = +0.0
@@ -100,17 +105,26 @@ __device__ __forceinline__ uint32_t step_index(uint32_t idx, uint32_t rel, uint3
   asm("{\n\t.reg .u32 t;\n\tadd.cc.u32 t, %2, %3;\n\taddc.u32 %0, %0, %1;\n\t}" : "+r"(idx) : "r"(rel), "r"(x), "r"(kv));
   return idx;
 }
+__device__ __forceinline__ uint32_t add_carry_out(uint32_t a, uint32_t b) {
+  uint32_t c;
+  asm("{\n\t.reg .u32 t;\n\tadd.cc.u32 t, %1, %2;\n\taddc.u32 %0, 0, 0;\n\t}" : "=r"(c) : "r"(a), "r"(b));
+  return c;
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t saddr) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr));
+  return v;
+}
 
-// Top of every tree in constant memory (Tunables::top_levels, default 4): the first 2^CTOP - 1 nodes of
-// a tree in breadth-first order are exactly its levels 0..CTOP-1.  Constant loads go through the
-// constant cache, not the LSU / TEX data pipes; lanes of a warp mostly agree at those levels, so the
-// per-address serialisation of divergent constant loads stays short.
-constexpr int kConstTopNodes = 7680;  // 61 440 B of the 64 KB constant bank (480 trees at 4 levels)
+// Top of every tree in constant memory: constant loads go through the constant cache, not the LSU / TEX
+// data pipes; lanes of a warp mostly agree at those levels, so the per-address serialisation of divergent
+// constant loads stays short.  The table belongs to one booster (and one range of its trees) at a time:
+//   8-byte-node walk: the first 2^CTOP - 1 nodes of a tree in breadth-first order = its levels 0..CTOP-1
+//   two-level records: DuoForest::top_xy (complete heap-ordered tops) + c_duo_base, the global index of each
+//                      tree's first record (the block pointers are tree-relative)
+constexpr int kConstTopNodes = kConstTreesMax << kDuoTop;  // 61 440 B of the 64 KB constant bank
 __constant__ uint2 c_top[kConstTopNodes];
-// two-level records: in that mode c_top holds DuoForest::top_xy (complete heap-ordered tops) instead, and
-// c_duo_base the global index of each tree's first record (the block pointers are tree-relative)
-constexpr int kConstDuoTrees = kConstTopNodes >> kDuoTop;
-__constant__ uint32_t c_duo_base[kConstDuoTrees];
+__constant__ uint32_t c_duo_base[kConstTreesMax];
 
 cudaError_t upload_const_top(const uint32_t *dev_nodes_xy, const uint32_t *tree_offset, int ntree, int levels, cudaStream_t s) {
   const int stride = 1 << levels;
@@ -127,17 +141,167 @@ cudaError_t upload_const_top(const uint32_t *dev_nodes_xy, const uint32_t *tree_
 }
 
 cudaError_t upload_const_duo(const uint32_t *top_xy, const uint32_t *tree_slot, int ntree, cudaStream_t s) {
-  if (ntree > kConstDuoTrees) return cudaErrorInvalidValue;
+  if (ntree > kConstTreesMax) return cudaErrorInvalidValue;
   cudaError_t e = cudaMemcpyToSymbolAsync(c_top, top_xy, sizeof(uint2) * ((size_t)ntree << kDuoTop), 0, cudaMemcpyHostToDevice, s);
   if (e != cudaSuccess) return e;
   return cudaMemcpyToSymbolAsync(c_duo_base, tree_slot, sizeof(uint32_t) * (size_t)ntree, 0, cudaMemcpyHostToDevice, s);
 }
 
+// ---- TMA (bulk async copy) + mbarrier helpers: global -> shared without the LSU ------------------
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_init_fence() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+
+// The tile loop shared by the predict kernels.  A CTA walks tiles blockIdx.x, + gridDim.x, ...: with a grid of
+// one CTA per tile that is the classic launch (the resident CTAs of an SM overlap each other's loads); with a
+// persistent grid and NBUF = 2 the next tile's bulk copy (TMA, cp.async.bulk completing on an mbarrier —
+// SASS UBLKCP + SYNCS) is in flight while this one is walked.  A tile is ncol KB of keys in its final
+// layout: no LSU instruction, no register, no arithmetic between HBM and the walk.  One thread issues the
+// copy and polls the mbarrier, the CTA then passes a barrier (256 threads polling one word showed up as
+// shared-memory bank-conflict wavefronts on the LSU data pipe, profiles/README.md v4).
+template <int NBUF>
+struct TilePipe {
+  uint32_t smem0, bar0, buf_bytes, tile_bytes;
+  const uint32_t *Xt;
+  uint64_t ntile, tile;
+  uint32_t it;
+  __device__ __forceinline__ void issue(uint64_t t, int b) const {
+    if (tile_bytes) {
+      mbar_expect_tx(bar0 + 8u * b, tile_bytes);
+      bulk_g2s(smem0 + buf_bytes * b, Xt + t * (uint64_t)(tile_bytes / 4), tile_bytes, bar0 + 8u * b);
+    } else {
+      mbar_expect_tx(bar0 + 8u * b, 0u);
+    }
+  }
+  // slots the matrix does not have are missing (xgboost FVec::Fill leaves them flagged); slot nfeat is the
+  // key-0 slot leaves point at.  Written once per buffer: the bulk copies only touch slots 0..ncol-1.
+  __device__ __forceinline__ void begin(uint32_t *smem, unsigned long long *bars, const PredictArgs &a, int nfeat, int tid) {
+    smem0 = (uint32_t)__cvta_generic_to_shared(smem), bar0 = (uint32_t)__cvta_generic_to_shared(bars);
+    buf_bytes = (uint32_t)(nfeat + 1) * kStride * 4u, tile_bytes = (uint32_t)a.ncol * kStride * 4u;
+    Xt = a.Xt, ntile = (a.nrow + kTileRows - 1) / kTileRows, tile = blockIdx.x, it = 0;
+#pragma unroll
+    for (int b = 0; b < NBUF; ++b) {
+      uint32_t *k = smem + (size_t)b * (nfeat + 1) * kStride;
+      for (int c = a.ncol; c < nfeat; ++c) k[c * kStride + tid] = kKeyMissing;
+      k[nfeat * kStride + tid] = 0u;
+    }
+    if (tid == 0) {
+#pragma unroll
+      for (int b = 0; b < NBUF; ++b) mbar_init(bar0 + 8u * b, 1);
+      mbar_init_fence();
+    }
+    __syncthreads();
+    if (tid == 0 && tile < ntile) issue(tile, 0);
+  }
+  __device__ __forceinline__ bool more() const { return tile < ntile; }
+  // returns the shared address of this iteration's tile
+  __device__ __forceinline__ uint32_t acquire(int tid) {
+    const int cur = NBUF == 2 ? (int)(it & 1u) : 0;
+    if (tid == 0) {
+      if (NBUF == 2 && tile + gridDim.x < ntile) issue(tile + gridDim.x, cur ^ 1);
+      mbar_wait(bar0 + 8u * cur, (it / NBUF) & 1u);
+    }
+    __syncthreads();
+    return smem0 + buf_bytes * cur;
+  }
+  __device__ __forceinline__ void release(int tid) {
+    // every thread is done with this buffer before it is refilled
+    if (NBUF == 2) {
+      if (tile + gridDim.x < ntile) __syncthreads();
+    } else if (tile + gridDim.x < ntile) {
+      __syncthreads();
+      if (tid == 0) issue(tile + gridDim.x, 0);
+    }
+    tile += gridDim.x, ++it;
+  }
+};
+
+// =====================================================================================
+// K3 — seal: row-major float matrix -> key tiles, with the missing / inf scan
+// =====================================================================================
+__global__ void __launch_bounds__(kTileRows) seal_tiles_kernel(const float *__restrict__ X, uint64_t nrow, int ncol, float missing,
+                                                               int check_inf, uint32_t *__restrict__ Xt, int *flags) {
+  extern __shared__ __align__(16) float srows[];  // [256][ld] row-major, ld odd: the per-thread row reads are conflict-free
+  const int tid = threadIdx.x;
+  const int ld = ncol | 1;
+  const uint64_t r0 = (uint64_t)blockIdx.x * kTileRows;
+  const uint64_t left = nrow - r0;
+  const int nr = left < (uint64_t)kTileRows ? (int)left : kTileRows;
+  const float *__restrict__ src = X + r0 * (uint64_t)ncol;
+  const int n = nr * ncol;
+  if (ld == ncol) {  // the tile's rows are one contiguous run of X: flat, coalesced copy
+    if ((((uintptr_t)src) & 15u) == 0u) {
+      const float4 *s4 = reinterpret_cast<const float4 *>(src);
+      float4 *d4 = reinterpret_cast<float4 *>(srows);
+      for (int i = tid; i < (n >> 2); i += kTileRows) d4[i] = __ldg(s4 + i);
+      for (int i = (n & ~3) + tid; i < n; i += kTileRows) srows[i] = __ldg(src + i);
+    } else {
+      for (int i = tid; i < n; i += kTileRows) srows[i] = __ldg(src + i);
+    }
+  } else {
+    for (int i = tid; i < n; i += kTileRows) srows[(i / ncol) * ld + (i % ncol)] = __ldg(src + i);
+  }
+  __syncthreads();
+  uint32_t *__restrict__ dst = Xt + (size_t)blockIdx.x * (size_t)ncol * kTileRows + tid;
+  int fl = 0;
+  for (int c = 0; c < ncol; ++c) {
+    uint32_t k = 0u;  // rows past the end of the matrix: any key (their results are never stored)
+    if (tid < nr) {
+      const float x = srows[tid * ld + c];
+      k = float_key(x);
+      if (x != x || x == missing) k = kKeyMissing, fl |= 1;
+      if (check_inf && isinf(x)) fl |= 2;
+    }
+    dst[(size_t)c * kTileRows] = k;  // 1 KB per column, coalesced
+  }
+  fl = __reduce_or_sync(0xffffffffu, fl);
+  if ((tid & 31) == 0 && fl) atomicOr(flags, fl);
+}
+
+cudaError_t launch_seal_tiles(const float *X, uint64_t nrow, int ncol, float missing, uint32_t *Xt, int *flags, cudaStream_t s) {
+  if (nrow == 0 || ncol == 0) return cudaSuccess;
+  const uint64_t ntile = tile_count(nrow);
+  if (ntile > 0x7fffffffull) return cudaErrorInvalidConfiguration;
+  const size_t smem = (size_t)kTileRows * (size_t)(ncol | 1) * sizeof(float);
+  cudaError_t e = cudaFuncSetAttribute(seal_tiles_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  // xgboost src/data/data.cc: `!std::isinf(missing) && std::isinf(value)` invalidates the input
+  seal_tiles_kernel<<<(unsigned)ntile, kTileRows, smem, s>>>(X, nrow, ncol, missing, std::isinf(missing) ? 0 : 1, Xt, flags);
+  count_family("seal_tiles", false, false);
+  return QC_LAUNCHED();
+}
+
+// =====================================================================================
+// K2 — walk on the 8-byte depth-ordered nodes
+// =====================================================================================
 // TEXMODE is a bit mask over the ILP trees in flight: tree j fetches its nodes through the texture pipe
-// (tex1Dfetch on the same buffer) if bit j is set, through the LSU (LDG) otherwise.
+// (tex1Dfetch on the same buffer) if bit j is set, through the LSU (LDG) otherwise.  ctree0: the first tree
+// the constant table holds.
 template <int ILP, bool HAS_MISSING, bool PARK, int TEXMODE = 0, int CTOP = 0>
 __device__ __forceinline__ void walk_group(const uint2 *__restrict__ nodes, cudaTextureObject_t tex, const uint32_t *__restrict__ toff,
-                                           const int32_t *__restrict__ tdepth, int t, uint32_t my_saddr,
+                                           const int32_t *__restrict__ tdepth, int t, int ctree0, uint32_t my_saddr,
                                            uint32_t (&idx)[ILP], uint32_t (&xbits)[ILP]) {
   int depth = 0, minleaf = 255;  // tdepth[] = deepest leaf | shallowest leaf << 8
   uint2 nd[ILP];
@@ -157,12 +321,10 @@ __device__ __forceinline__ void walk_group(const uint2 *__restrict__ nodes, cuda
   // lines per warp request; the L1TEX data pipe is the bound of this kernel.  The
   // fetch is predicated, so nd[j] keeps the leaf node and no per-level copy of the value is needed.
   auto visit = [&](int j) {
-    // shared address of srow[feat][tid] = my_saddr + feat * (kBlock * 4): the top byte of the meta word
+    // shared address of skey[feat][tid] = my_saddr + feat * 1024: the top byte of the meta word
     // is feat * 4, so moving it to byte 1 (one PRMT) gives feat * 1024
-    static_assert(kStride * 4 == 1024 && kBlock <= kStride && kMetaFeatShift == 26, "address trick assumes a 1 KB feature stride");
-    const uint32_t sa = my_saddr + __byte_perm(nd[j].y, 0u, 0x4434);
-    uint32_t kv;
-    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(kv) : "r"(sa));
+    static_assert(kMetaFeatShift == 26, "address trick assumes feat in the top 6 bits");
+    const uint32_t kv = lds_u32(my_saddr + __byte_perm(nd[j].y, 0u, 0x4434));
     rel[j] = nd[j].y & kMetaRelMask;
     if (HAS_MISSING && kv == kKeyMissing)  // default child: left = idx + rel, right = left + 1
       idx[j] += rel[j] + ((nd[j].y & kMetaDefaultLeftBit) ? 0u : (rel[j] != 0u ? 1u : 0u));
@@ -172,7 +334,7 @@ __device__ __forceinline__ void walk_group(const uint2 *__restrict__ nodes, cuda
   if (CTOP > 0) {
     uint32_t cbase[ILP];  // index of this tree's table row minus its first node
 #pragma unroll
-    for (int j = 0; j < ILP; ++j) cbase[j] = ((uint32_t)(t + j) << CTOP) - idx[j];
+    for (int j = 0; j < ILP; ++j) cbase[j] = ((uint32_t)(t + j - ctree0) << CTOP) - idx[j];
     if (minleaf >= CTOP) {
       // no leaf above level CTOP in any of these trees (the usual case for deep trees): every lane walks
       // all CTOP levels — no park predicate, no branches
@@ -218,24 +380,41 @@ __device__ __forceinline__ void walk_group(const uint2 *__restrict__ nodes, cuda
   for (int j = 0; j < ILP; ++j) xbits[j] = nd[j].x;
 }
 
-// ---- two levels per gather (forest.hpp DuoForest) -----------------------------------------------------
-// Levels 0..3 come from constant memory as above (every tree of a qualifying booster has no leaf there, so
-// the prologue is branch-free); from level 4 on one 16-byte record {root, left, right thresholds; features;
-// block pointer} decides two levels, and the four possible successors are contiguous.  Against the 8-byte
-// nodes this halves the dependent gathers of a walk and takes ~40 % of the distinct lines per warp request
-// off the L1TEX data pipes (tools/replay_two_level_records.py).  Clean matrix (no missing entry) only.
-__device__ __forceinline__ uint32_t add_carry_out(uint32_t a, uint32_t b) {
-  uint32_t c;
-  asm("{\n\t.reg .u32 t;\n\tadd.cc.u32 t, %1, %2;\n\taddc.u32 %0, 0, 0;\n\t}" : "=r"(c) : "r"(a), "r"(b));
-  return c;
+// all trees [t0, t1) on the 8-byte nodes, in tree order; emit(t, value bits, node index)
+template <int ILP, bool HAS_MISSING, bool PARK, int TEXMODE, int CTOP, class Emit>
+__device__ __forceinline__ void forest_walk(const DeviceForest &f, uint32_t my, int t0, int t1, Emit &&emit) {
+  int t = t0;
+  for (; t + ILP <= t1; t += ILP) {
+    uint32_t idx[ILP], xb[ILP];
+    walk_group<ILP, HAS_MISSING, PARK, TEXMODE, CTOP>(f.nodes, f.tex, f.tree_offset, f.tree_depth, t, f.const_tree0, my, idx, xb);
+#pragma unroll
+    for (int j = 0; j < ILP; ++j) emit(t + j, xb[j], idx[j]);
+  }
+  for (; t < t1; ++t) {
+    uint32_t idx[1], xb[1];
+    walk_group<1, HAS_MISSING, PARK, 0, 0>(f.nodes, f.tex, f.tree_offset, f.tree_depth, t, 0, my, idx, xb);
+    emit(t, xb[0], idx[0]);
+  }
 }
+
+// =====================================================================================
+// K2b — walk on the two-level records (forest.hpp DuoForest)
+// =====================================================================================
+// Levels 0..3 come from constant memory as complete heap-ordered tops (entry i, children 2i and 2i + 1: no
+// branch, no predicate); from level 4 on one 16-byte record {root, left, right thresholds; features; block
+// pointer} decides two levels, and the four possible successors are contiguous.  Against the 8-byte nodes
+// this halves the dependent gathers of a walk and takes ~40 % of the distinct lines per warp request off the
+// L1TEX data pipes (tools/replay_two_level_records.py).
 // Default shape (B200, profiles/README.md "two-level records"): 6 trees in flight, 4 of them gathering through
-// the texture pipe, 5 resident CTAs per SM (45 registers) — LSU and TEX data pipes, ALU and issue slots all end
-// up at 76-84 % busy.
+// the texture pipe, 5 resident CTAs per SM — LSU and TEX data pipes, ALU and issue slots all end up at
+// 76-86 % busy.
+// HAS_MISSING: a missing entry (key 0xFFFFFFFF) takes the node's default child (bits 17..15 of w3 / bit 0 of a
+// top entry's y word); the records carry those bits when DeviceForest::duo_has_dl.
 constexpr int kDuoIlp = 6, kDuoTexMask = 0x36, kDuoMinBlocks = 5;
-template <int ILP, int TEXMODE>
+template <int ILP, int TEXMODE, bool HAS_MISSING>
 __device__ __forceinline__ void walk_group_duo(const uint4 *__restrict__ recs, cudaTextureObject_t tex4,
-                                               const int32_t *__restrict__ tdepth, int t, uint32_t my_saddr, uint32_t (&xbits)[ILP]) {
+                                               const int32_t *__restrict__ tdepth, uint32_t blk_mul, int t, int ctree0, uint32_t my_saddr,
+                                               uint32_t (&xbits)[ILP], uint32_t (&ids)[ILP]) {
   constexpr int CTOP = kDuoTop;
   int depth = CTOP - 1;  // at least one record (a shallower tree ends in the terminal records of its padded leaves)
   uint32_t idx[ILP];
@@ -244,22 +423,27 @@ __device__ __forceinline__ void walk_group_duo(const uint4 *__restrict__ recs, c
     depth = max(depth, __ldg(tdepth + t + j) & 0xFF);
     idx[j] = 1u;  // heap position in the complete top: children of i are 2i and 2i + 1
   }
+  const int tl = t - ctree0;  // row of the constant tables
 #pragma unroll
   for (int d = 0; d < CTOP; ++d) {
 #pragma unroll
     for (int j = 0; j < ILP; ++j) {
-      const uint2 nd = c_top[((uint32_t)(t + j) << CTOP) + idx[j]];
-      const uint32_t sa = my_saddr + __byte_perm(nd.y, 0u, 0x4434);
-      uint32_t kv;
-      asm volatile("ld.shared.u32 %0, [%1];" : "=r"(kv) : "r"(sa));
-      idx[j] = step_index(idx[j], idx[j], nd.x, kv);  // 2i + right
+      const uint2 nd = c_top[((uint32_t)(tl + j) << CTOP) + idx[j]];
+      const uint32_t kv = lds_u32(my_saddr + __byte_perm(nd.y, 0u, 0x4434));
+      if (HAS_MISSING) {
+        uint32_t right = add_carry_out(nd.x, kv);
+        if (kv == kKeyMissing) right = (nd.y & kTopDefaultLeftBit) ^ 1u;
+        idx[j] = 2u * idx[j] + right;
+      } else {
+        idx[j] = step_index(idx[j], idx[j], nd.x, kv);  // 2i + right
+      }
     }
   }
   uint4 r[ILP];
   uint32_t walking[ILP];
 #pragma unroll
   for (int j = 0; j < ILP; ++j) {
-    idx[j] += c_duo_base[t + j] - (1u << CTOP);  // heap position 16..31 -> record index
+    idx[j] += c_duo_base[tl + j] - (1u << CTOP);  // heap position 16..31 -> record index
     r[j] = make_uint4(0u, 0u, 0u, 0u);
     walking[j] = 1u;
   }
@@ -280,35 +464,72 @@ __device__ __forceinline__ void walk_group_duo(const uint4 *__restrict__ recs, c
     uint32_t kv0[ILP], kv[ILP], right1[ILP];
 #pragma unroll
     for (int j = 0; j < ILP; ++j) {
-      // srow[feat(root)][tid]: feat is the low 5 bits of w3; one AND + one multiply-add
+      // skey[feat(root)][tid]: feat is the low 5 bits of w3; one AND + one multiply-add
       uint32_t sa;
       asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(sa) : "r"(r[j].w & 31u), "r"((uint32_t)(kStride * 4)), "r"(my_saddr));
-      asm volatile("ld.shared.u32 %0, [%1];" : "=r"(kv0[j]) : "r"(sa));
+      kv0[j] = lds_u32(sa);
     }
 #pragma unroll
     for (int j = 0; j < ILP; ++j) {
       right1[j] = add_carry_out(r[j].x, kv0[j]);
+      if (HAS_MISSING && kv0[j] == kKeyMissing) right1[j] = (r[j].w & kDuoDlRoot) ? 0u : 1u;
       // feat(left) sits at bits 14..10 — already feat * 1024 —, feat(right) at 9..5
       const uint32_t ms = right1[j] ? (r[j].w << 5) : r[j].w;
-      asm volatile("ld.shared.u32 %0, [%1];" : "=r"(kv[j]) : "r"(my_saddr + (ms & (31u << 10))));
+      kv[j] = lds_u32(my_saddr + (ms & (31u << 10)));
     }
 #pragma unroll
     for (int j = 0; j < ILP; ++j) {
       const uint32_t xs = right1[j] ? r[j].z : r[j].y;
-      // blk = w3 >> 15 as a multiply-high: the FMA pipe has room, the ALU pipe (SEL / LOP3 / IADD3) does not
+      // blk = w3 >> blk_shift as a multiply-high: the FMA pipe has room, the ALU pipe (SEL / LOP3 / IADD3) does not
       uint32_t blk;
-      asm("mul.hi.u32 %0, %1, %2;" : "=r"(blk) : "r"(r[j].w), "r"(1u << (32 - kDuoBlkShift)));
-      // next record = base + blk * 4 + 2 * right1 + right2
-      // half = 2 * blk + right1, the carry of the root compare folded into a multiply-add (FMA pipe again)
-      uint32_t half;
-      asm("{\n\t.reg .u32 t;\n\tadd.cc.u32 t, %1, %2;\n\tmadc.lo.u32 %0, %3, 2, 0;\n\t}" : "=r"(half) : "r"(r[j].x), "r"(kv0[j]), "r"(blk));
-      idx[j] = step_index(c_duo_base[t + j] + half, half, xs, kv[j]);
+      asm("mul.hi.u32 %0, %1, %2;" : "=r"(blk) : "r"(r[j].w), "r"(blk_mul));
+      if (HAS_MISSING) {
+        uint32_t right2 = add_carry_out(xs, kv[j]);
+        // a leaf child compares the key-0 slot: never missing.  Default bit of the child that was taken.
+        if (kv[j] == kKeyMissing) right2 = (r[j].w & (right1[j] ? kDuoDlRight : kDuoDlLeft)) ? 0u : 1u;
+        const uint32_t half = 2u * blk + right1[j];
+        idx[j] = c_duo_base[tl + j] + 2u * half + right2;
+      } else {
+        // next record = base + blk * 4 + 2 * right1 + right2
+        // half = 2 * blk + right1, the carry of the root compare folded into a multiply-add (FMA pipe again)
+        uint32_t half;
+        asm("{\n\t.reg .u32 t;\n\tadd.cc.u32 t, %1, %2;\n\tmadc.lo.u32 %0, %3, 2, 0;\n\t}" : "=r"(half) : "r"(r[j].x), "r"(kv0[j]), "r"(blk));
+        idx[j] = step_index(c_duo_base[tl + j] + half, half, xs, kv[j]);
+      }
       walking[j] = blk;  // 0: this was a terminal record, r[j].x is the leaf value
       asm volatile("" : "+r"(walking[j]));
     }
   }
 #pragma unroll
-  for (int j = 0; j < ILP; ++j) xbits[j] = r[j].x;
+  for (int j = 0; j < ILP; ++j) xbits[j] = r[j].x, ids[j] = r[j].y;
+}
+
+// all trees [t0, t1) on the two-level records: ILP-wide groups, then half-width groups (one LSU tree, the rest on
+// the texture pipe), then one by one — always in tree order (float32 sum order is part of parity).
+// emit(t, leaf value bits, XGBoost node id of the leaf)
+template <int ILP, int TEXMODE, bool HAS_MISSING, class Emit>
+__device__ __forceinline__ void forest_walk_duo(const DeviceForest &f, uint32_t my, int t0, int t1, Emit &&emit) {
+  int t = t0;
+  for (; t + ILP <= t1; t += ILP) {
+    uint32_t xb[ILP], id[ILP];
+    walk_group_duo<ILP, TEXMODE, HAS_MISSING>(f.recs, f.tex4, f.tree_depth, f.duo_blk_mul, t, f.const_tree0, my, xb, id);
+#pragma unroll
+    for (int j = 0; j < ILP; ++j) emit(t + j, xb[j], id[j]);
+  }
+  constexpr int H = ILP / 2;
+  if (H >= 2) {
+    for (; t + H <= t1; t += H) {
+      uint32_t xb[H > 0 ? H : 1], id[H > 0 ? H : 1];
+      walk_group_duo<(H > 0 ? H : 1), ((1 << H) - 2), HAS_MISSING>(f.recs, f.tex4, f.tree_depth, f.duo_blk_mul, t, f.const_tree0, my, xb, id);
+#pragma unroll
+      for (int j = 0; j < H; ++j) emit(t + j, xb[j], id[j]);
+    }
+  }
+  for (; t < t1; ++t) {
+    uint32_t xb[1], id[1];
+    walk_group_duo<1, 0, HAS_MISSING>(f.recs, f.tex4, f.tree_depth, f.duo_blk_mul, t, f.const_tree0, my, xb, id);
+    emit(t, xb[0], id[0]);
+  }
 }
 
 __device__ __forceinline__ float export_transform(float acc, int exp10_on, float scale) {
@@ -319,167 +540,57 @@ __device__ __forceinline__ float export_transform(float acc, int exp10_on, float
   return __fmul_rn(p, scale);
 }
 
-// ---- TMA (bulk async copy) + mbarrier helpers: global -> shared without the LSU ------------------
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-               "l"(src), "r"(bytes), "r"(bar)
-               : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "WAIT_%=:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra DONE_%=;\n"
-      "bra WAIT_%=;\n"
-      "DONE_%=:\n"
-      "}\n" ::"r"(bar),
-      "r"(parity)
-      : "memory");
-}
-
-// Stage the CTA's rows (one contiguous run of X) into the transposed key tile srow[f][tid].
-template <bool HAS_MISSING>
-__device__ __forceinline__ void stage_tile(float *srow, unsigned long long *tile_bar, const PredictArgs &a, int nfeat, int tid,
-                                           uint64_t r0, int nr) {
-  uint32_t *skey = reinterpret_cast<uint32_t *>(srow);  // the transposed tile holds keys, not floats
-  constexpr int B = kBlock;
-  const int ncol = a.ncol;
-  // stage 1: the tile's rows are one contiguous run of X.  Full, 16-byte aligned tiles come in with a
-  // single bulk async copy (TMA, cp.async.bulk) completing on an mbarrier — no LSU instructions, no
-  // registers; the ragged tail tile (or a misaligned matrix) falls back to a coalesced LDG/STS loop.
-  const float *__restrict__ src = a.X + r0 * (uint64_t)ncol;
-  const int n = nr * ncol;
-  const uint32_t bytes = (uint32_t)n * 4u;
-  const bool bulk = ((bytes | (uint32_t)(uintptr_t)src) & 15u) == 0u;
-  if (bulk) {
-    const uint32_t bar = (uint32_t)__cvta_generic_to_shared(tile_bar);
-    if (tid == 0) mbar_init(bar, 1);
-    __syncthreads();
-    if (tid == 0) {
-      mbar_expect_tx(bar, bytes);
-      bulk_g2s((uint32_t)__cvta_generic_to_shared(srow), src, bytes, bar);
-      // one thread polls the mbarrier; 256 threads polling the same word showed up as 1.15 G
-      // shared-memory bank-conflict wavefronts on the LSU data pipe (profiles/README.md, v4)
-      mbar_wait(bar, 0);
-    }
-    __syncthreads();
+// what a row does with its leaves: float32 sum in tree order (+ export transform on the last launch of a
+// chunked forest), or the leaf's XGBoost node id per tree (option_mask = 2)
+template <bool PRED_LEAF, class Walk>
+__device__ __forceinline__ void row_result(const DeviceForest &f, const PredictArgs &a, uint64_t row, bool live, Walk &&walk) {
+  if (PRED_LEAF) {
+    float *o = a.out + row * (uint64_t)a.out_stride;
+    walk([&](int t, uint32_t, uint32_t id) {
+      if (live) o[t] = (float)id;
+    });
   } else {
-    for (int i = tid; i < n; i += B) srow[i] = __ldg(src + i);
-    __syncthreads();
+    float acc = f.base_score;
+    if (!a.first && live) acc = a.out[row];
+    walk([&](int, uint32_t xb, uint32_t) { acc = __fadd_rn(acc, __uint_as_float(xb)); });
+    if (live) a.out[row] = a.last ? export_transform(acc, a.exp10, a.scale) : acc;
   }
-  // stage 2: each thread lifts its own row into registers (stride ncol: conflict-free for the
-  // 27-column matrix), then writes it back transposed
-  float v[32];
-  const int nc32 = ncol < 32 ? ncol : 32;
-#pragma unroll
-  for (int c = 0; c < 32; ++c) v[c] = (c < nc32 && tid < nr) ? srow[tid * ncol + c] : 0.f;
-  __syncthreads();
-#pragma unroll
-  for (int c = 0; c < 32; ++c)
-    if (c < nc32) {
-      const float x = v[c];
-      uint32_t k = float_key(x);
-      if (HAS_MISSING && (x != x || x == a.missing)) k = kKeyMissing;
-      skey[c * kStride + tid] = k;
-    }
-  // columns the matrix does not have are missing (xgboost FVec::Fill leaves them flagged)
-  for (int c = nc32; c < nfeat; ++c) skey[c * kStride + tid] = kKeyMissing;
-  skey[nfeat * kStride + tid] = 0u;
 }
 
-template <int ILP, bool HAS_MISSING, bool PRED_LEAF, bool PARK, int MINB, int TEXMODE = 0, int CTOP = 0>
-__global__ void __launch_bounds__(kBlock, MINB) predict_rows_kernel(DeviceForest f, PredictArgs a) {
-  extern __shared__ __align__(128) float srow[];
-  __shared__ __align__(8) unsigned long long tile_bar;
+template <int ILP, int MINB, int TEXMODE, bool HAS_MISSING, bool PRED_LEAF, int NBUF>
+__global__ void __launch_bounds__(kBlock, MINB) predict_tiles_kernel(DeviceForest f, PredictArgs a) {
+  extern __shared__ __align__(128) uint32_t skey[];
+  __shared__ __align__(8) unsigned long long bars[NBUF];
   const int tid = threadIdx.x;
-  constexpr int B = kBlock;
-  const uint64_t r0 = (uint64_t)blockIdx.x * B;
-  const uint64_t left = a.nrow - r0;
-  const int nr = left < (uint64_t)B ? (int)left : B;
-  stage_tile<HAS_MISSING>(srow, &tile_bar, a, f.nfeat, tid, r0, nr);
-  if (tid >= nr) return;
-  const bool live = true;
-  const uint32_t my = (uint32_t)__cvta_generic_to_shared(srow + tid);
-  const uint64_t row = r0 + tid;
-  const int ntree = a.ntree_used;
-  float acc = f.base_score;
-  int t = 0;
-  for (; t + ILP <= ntree; t += ILP) {
-    uint32_t idx[ILP], xb[ILP];
-    walk_group<ILP, HAS_MISSING, PARK, TEXMODE, CTOP>(f.nodes, f.tex, f.tree_offset, f.tree_depth, t, my, idx, xb);
-#pragma unroll
-    for (int j = 0; j < ILP; ++j) {
-      if (PRED_LEAF) {
-        if (live) a.out[row * (uint64_t)ntree + t + j] = (float)__ldg(f.orig_id + idx[j]);
-      } else {
-        acc = __fadd_rn(acc, __uint_as_float(xb[j]));
-      }
-    }
+  TilePipe<NBUF> pipe;
+  pipe.begin(skey, bars, a, f.nfeat, tid);
+  while (pipe.more()) {
+    const uint32_t my = pipe.acquire(tid) + 4u * (uint32_t)tid;
+    const uint64_t row = pipe.tile * kTileRows + tid;
+    row_result<PRED_LEAF>(f, a, row, row < a.nrow, [&](auto &&emit) {
+      forest_walk_duo<ILP, TEXMODE, HAS_MISSING>(f, my, a.tree_begin, a.tree_end, emit);
+    });
+    pipe.release(tid);
   }
-  for (; t < ntree; ++t) {
-    uint32_t idx[1], xb[1];
-    walk_group<1, HAS_MISSING, PARK, 0>(f.nodes, f.tex, f.tree_offset, f.tree_depth, t, my, idx, xb);
-    if (PRED_LEAF) {
-      if (live) a.out[row * (uint64_t)ntree + t] = (float)__ldg(f.orig_id + idx[0]);
-    } else {
-      acc = __fadd_rn(acc, __uint_as_float(xb[0]));
-    }
-  }
-  if (!PRED_LEAF && live) a.out[row] = export_transform(acc, a.exp10, a.scale);
 }
 
-// all trees of the forest on the two-level records: ILP-wide groups, then half-width groups (one LSU tree,
-// the rest on the texture pipe), then one by one — always in tree order (float32 sum order is part of parity)
-template <int ILP, int TEXMODE>
-__device__ __forceinline__ float forest_sum_duo(const DeviceForest &f, uint32_t my, int ntree) {
-  float acc = f.base_score;
-  int t = 0;
-  for (; t + ILP <= ntree; t += ILP) {
-    uint32_t xb[ILP];
-    walk_group_duo<ILP, TEXMODE>(f.recs, f.tex4, f.tree_depth, t, my, xb);
-#pragma unroll
-    for (int j = 0; j < ILP; ++j) acc = __fadd_rn(acc, __uint_as_float(xb[j]));
-  }
-  constexpr int H = ILP / 2;
-  if (H >= 2) {
-    for (; t + H <= ntree; t += H) {
-      uint32_t xb[H > 0 ? H : 1];
-      walk_group_duo<(H > 0 ? H : 1), ((1 << H) - 2)>(f.recs, f.tex4, f.tree_depth, t, my, xb);
-#pragma unroll
-      for (int j = 0; j < H; ++j) acc = __fadd_rn(acc, __uint_as_float(xb[j]));
-    }
-  }
-  for (; t < ntree; ++t) {
-    uint32_t xb[1];
-    walk_group_duo<1, 0>(f.recs, f.tex4, f.tree_depth, t, my, xb);
-    acc = __fadd_rn(acc, __uint_as_float(xb[0]));
-  }
-  return acc;
-}
-
-// predict_rows_kernel's clean-matrix / sums case on the two-level records
-template <int ILP, int MINB, int TEXMODE>
-__global__ void __launch_bounds__(kBlock, MINB) predict_rows_duo_kernel(DeviceForest f, PredictArgs a) {
-  extern __shared__ __align__(128) float srow[];
-  __shared__ __align__(8) unsigned long long tile_bar;
+template <int ILP, bool HAS_MISSING, bool PRED_LEAF, bool PARK, int MINB, int TEXMODE, int CTOP>
+__global__ void __launch_bounds__(kBlock, MINB) predict_tiles_nodes8_kernel(DeviceForest f, PredictArgs a) {
+  extern __shared__ __align__(128) uint32_t skey[];
+  __shared__ __align__(8) unsigned long long bars[1];
   const int tid = threadIdx.x;
-  const uint64_t r0 = (uint64_t)blockIdx.x * kBlock;
-  const uint64_t left = a.nrow - r0;
-  const int nr = left < (uint64_t)kBlock ? (int)left : kBlock;
-  stage_tile<false>(srow, &tile_bar, a, f.nfeat, tid, r0, nr);
-  if (tid >= nr) return;
-  const uint32_t my = (uint32_t)__cvta_generic_to_shared(srow + tid);
-  const float acc = forest_sum_duo<ILP, TEXMODE>(f, my, a.ntree_used);
-  a.out[r0 + tid] = export_transform(acc, a.exp10, a.scale);
+  TilePipe<1> pipe;
+  pipe.begin(skey, bars, a, f.nfeat, tid);
+  while (pipe.more()) {
+    const uint32_t my = pipe.acquire(tid) + 4u * (uint32_t)tid;
+    const uint64_t row = pipe.tile * kTileRows + tid;
+    row_result<PRED_LEAF>(f, a, row, row < a.nrow, [&](auto &&emit) {
+      forest_walk<ILP, HAS_MISSING, PARK, TEXMODE, CTOP>(f, my, a.tree_begin, a.tree_end, [&](int t, uint32_t xb, uint32_t idx) {
+        emit(t, xb, PRED_LEAF ? (uint32_t)__ldg(f.orig_id + idx) : 0u);
+      });
+    });
+    pipe.release(tid);
+  }
 }
 
 // ---- fused Run1 variant: the tile is assembled straight from the SoA feature fields ------------------
@@ -488,30 +599,11 @@ __global__ void __launch_bounds__(kBlock, MINB) predict_rows_duo_kernel(DeviceFo
 // field, so every load is coalesced and lands directly in the transposed tile — the [N x 27] matrix is
 // never formed, and no transposition is needed.  Whether a tile holds missing entries is decided per
 // tile (block-wide OR) and selects the walk specialisation at run time; +-inf raises the error flag.
-template <int ILP, bool HAS_MISSING, bool PARK, int TEXMODE, int CTOP>
-__device__ __forceinline__ float forest_sum(const DeviceForest &f, uint32_t my, int ntree) {
-  float acc = f.base_score;
-  int t = 0;
-  for (; t + ILP <= ntree; t += ILP) {
-    uint32_t idx[ILP], xb[ILP];
-    walk_group<ILP, HAS_MISSING, PARK, TEXMODE, CTOP>(f.nodes, f.tex, f.tree_offset, f.tree_depth, t, my, idx, xb);
-#pragma unroll
-    for (int j = 0; j < ILP; ++j) acc = __fadd_rn(acc, __uint_as_float(xb[j]));
-  }
-  for (; t < ntree; ++t) {
-    uint32_t idx[1], xb[1];
-    walk_group<1, HAS_MISSING, PARK, 0>(f.nodes, f.tex, f.tree_offset, f.tree_depth, t, my, idx, xb);
-    acc = __fadd_rn(acc, __uint_as_float(xb[0]));
-  }
-  return acc;
-}
-
-// DUO: clean tiles walk the two-level records (the constant table then holds the heap-ordered tops, so a tile
-// with missing entries walks the 8-byte nodes without a table: CTOP must be 0).
+// DUO: the constant table holds the heap-ordered tops of the two-level records; a tile with missing entries
+// walks them too when they carry the default bits, else the 8-byte nodes without a table (CTOP must be 0).
 template <int TEXMODE, int CTOP, bool DUO = false>
 __global__ void __launch_bounds__(kBlock, DUO ? kDuoMinBlocks : 6) predict_soa_kernel(DeviceForest f, SoaArgs a) {
-  extern __shared__ __align__(128) float srow[];
-  uint32_t *skey = reinterpret_cast<uint32_t *>(srow);
+  extern __shared__ __align__(128) uint32_t skey[];
   const int tid = threadIdx.x;
   constexpr int B = kBlock;
   const uint64_t m = (uint64_t)blockIdx.x * B + tid;
@@ -544,14 +636,19 @@ __global__ void __launch_bounds__(kBlock, DUO ? kDuoMinBlocks : 6) predict_soa_k
     if (tid == 0) atomicOr(a.flags, 2);
   }
   if (!live) return;
-  const uint32_t my = (uint32_t)__cvta_generic_to_shared(srow + tid);
-  float acc;
-  if (tile_missing)
-    acc = forest_sum<4, true, true, TEXMODE, CTOP>(f, my, a.ntree_used);
-  else if (DUO)
-    acc = forest_sum_duo<kDuoIlp, kDuoTexMask>(f, my, a.ntree_used);
-  else
-    acc = forest_sum<4, false, true, TEXMODE, CTOP>(f, my, a.ntree_used);
+  const uint32_t my = (uint32_t)__cvta_generic_to_shared(skey + tid);
+  float acc = f.base_score;
+  auto add = [&](int, uint32_t xb, uint32_t) { acc = __fadd_rn(acc, __uint_as_float(xb)); };
+  if (DUO && (!tile_missing || f.duo_has_dl)) {
+    if (tile_missing)
+      forest_walk_duo<kDuoIlp, kDuoTexMask, true>(f, my, 0, a.ntree_used, add);
+    else
+      forest_walk_duo<kDuoIlp, kDuoTexMask, false>(f, my, 0, a.ntree_used, add);
+  } else if (tile_missing) {
+    forest_walk<4, true, true, TEXMODE, CTOP>(f, my, 0, a.ntree_used, add);
+  } else {
+    forest_walk<4, false, true, TEXMODE, CTOP>(f, my, 0, a.ntree_used, add);
+  }
   if (a.pred) a.pred[m] = acc;
   a.out[m] = export_transform(acc, a.exp10, a.scale);
 }
@@ -563,101 +660,124 @@ cudaError_t launch_predict_soa(const DeviceForest &f, const SoaArgs &a, const Tu
   const uint64_t nblk = (a.nrow + kBlock - 1) / kBlock;
   if (nblk > 0x7fffffffull) return cudaErrorInvalidConfiguration;
   const bool tex = f.tex != 0 && t.variant >= 0;
+  const bool duo = f.duo_ready && f.const_tree0 == 0 && f.const_ntree >= a.ntree_used;
   auto k = !tex ? predict_soa_kernel<0, 0> : (f.const_top_levels == 4 ? predict_soa_kernel<0xA, 4> : predict_soa_kernel<0xA, 0>);
-  if (f.duo_ready) k = predict_soa_kernel<0xA, 0, true>;
+  if (duo) k = predict_soa_kernel<0xA, 0, true>;
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   k<<<dim3((unsigned)nblk), kBlock, smem, s>>>(f, a);
+  count_family(duo ? "soa_duo" : "soa_nodes8", false, false);
   return QC_LAUNCHED();
 }
 
-template <int ILP, bool HM, bool PL, bool PARK, int MINB, int TEXMODE = 0, int CTOP = 0>
-static cudaError_t launch_predict_one(const DeviceForest &f, const PredictArgs &a, cudaStream_t s) {
-  // srow holds max(ncol, nfeat + 1) feature slots per thread
-  const int slots = (f.nfeat + 1) > a.ncol ? (f.nfeat + 1) : a.ncol;
-  const size_t smem = (size_t)kStride * slots * sizeof(float);
-  const uint64_t nblk = (a.nrow + kBlock - 1) / kBlock;
-  if (nblk > 0x7fffffffull) return cudaErrorInvalidConfiguration;
-  auto k = predict_rows_kernel<ILP, HM, PL, PARK, MINB, TEXMODE, CTOP>;
+// ---- launches ------------------------------------------------------------------------------------------
+static int g_sm_count = 0;
+static int sm_count() {
+  if (g_sm_count == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || g_sm_count <= 0) g_sm_count = 148;
+  }
+  return g_sm_count;
+}
+
+template <class K>
+static cudaError_t launch_tiles(K k, const DeviceForest &f, const PredictArgs &a, int nbuf, int persistent_ctas_per_sm, cudaStream_t s) {
+  const size_t smem = (size_t)nbuf * kStride * (size_t)(f.nfeat + 1) * sizeof(uint32_t);
+  const uint64_t ntile = tile_count(a.nrow);
+  uint64_t grid = ntile;
+  if (persistent_ctas_per_sm > 0) grid = std::min<uint64_t>(ntile, (uint64_t)sm_count() * persistent_ctas_per_sm);
+  if (grid > 0x7fffffffull) return cudaErrorInvalidConfiguration;
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  k<<<dim3((unsigned)nblk), kBlock, smem, s>>>(f, a);
+  k<<<dim3((unsigned)grid), kBlock, smem, s>>>(f, a);
   return QC_LAUNCHED();
 }
 
-template <int ILP, int MINB, int TEXMODE>
-static cudaError_t launch_predict_duo(const DeviceForest &f, const PredictArgs &a, cudaStream_t s) {
-  const int slots = (f.nfeat + 1) > a.ncol ? (f.nfeat + 1) : a.ncol;
-  const size_t smem = (size_t)kStride * slots * sizeof(float);
-  const uint64_t nblk = (a.nrow + kBlock - 1) / kBlock;
-  if (nblk > 0x7fffffffull) return cudaErrorInvalidConfiguration;
-  auto k = predict_rows_duo_kernel<ILP, MINB, TEXMODE>;
-  cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
-  k<<<dim3((unsigned)nblk), kBlock, smem, s>>>(f, a);
-  return QC_LAUNCHED();
+// two-level records, default shape; HM / PL chosen at run time
+template <int ILP, int MINB, int TEXMODE, int NBUF>
+static cudaError_t launch_duo(const DeviceForest &f, const PredictArgs &a, int persistent, cudaStream_t s) {
+  const bool hm = a.has_missing != 0, pl = a.pred_leaf != 0;
+  if (hm && pl) return launch_tiles(predict_tiles_kernel<ILP, MINB, TEXMODE, true, true, NBUF>, f, a, NBUF, persistent, s);
+  if (hm) return launch_tiles(predict_tiles_kernel<ILP, MINB, TEXMODE, true, false, NBUF>, f, a, NBUF, persistent, s);
+  if (pl) return launch_tiles(predict_tiles_kernel<ILP, MINB, TEXMODE, false, true, NBUF>, f, a, NBUF, persistent, s);
+  return launch_tiles(predict_tiles_kernel<ILP, MINB, TEXMODE, false, false, NBUF>, f, a, NBUF, persistent, s);
 }
+
+template <int ILP, bool PARK, int MINB, int TEXMODE, int CTOP>
+static cudaError_t launch_nodes8(const DeviceForest &f, const PredictArgs &a, cudaStream_t s) {
+  const bool hm = a.has_missing != 0, pl = a.pred_leaf != 0;
+  if (hm && pl) return launch_tiles(predict_tiles_nodes8_kernel<ILP, true, true, PARK, MINB, TEXMODE, CTOP>, f, a, 1, 0, s);
+  if (hm) return launch_tiles(predict_tiles_nodes8_kernel<ILP, true, false, PARK, MINB, TEXMODE, CTOP>, f, a, 1, 0, s);
+  if (pl) return launch_tiles(predict_tiles_nodes8_kernel<ILP, false, true, PARK, MINB, TEXMODE, CTOP>, f, a, 1, 0, s);
+  return launch_tiles(predict_tiles_nodes8_kernel<ILP, false, false, PARK, MINB, TEXMODE, CTOP>, f, a, 1, 0, s);
+}
+
+// A forest is "shallow" when a row's walk is short enough for the tile stream to matter (the HBM-bound end of the
+// booster sweep, profiles/): those launches run persistent with a double-buffered TMA prefetch.
+// Two 28 KB buffers per CTA: three CTAs per SM (four would need 64 bytes more than the SM's 228 KB once the 1 KB
+// the system reserves per CTA is counted).
+constexpr int64_t kShallowSumDepth = 400;
+constexpr int kPersistCtasPerSm = 3;
 
 cudaError_t launch_predict(const DeviceForest &f, const PredictArgs &a, const Tunables &t, cudaStream_t s) {
-  if (a.nrow == 0) return cudaSuccess;
-  if (a.ncol > 32 || f.nfeat > 31) return cudaErrorInvalidValue;  // staged through 32 registers (forest.hpp kMaxFeatures)
-  // Default build: 4 trees in flight per thread; levels 0..3 of every tree come from constant memory;
-  // below that, trees 1 and 3 of each group fetch their nodes through the texture pipe and trees 0 and
-  // 2 through the LSU (mask 0xA).  The kernel is bound by the L1TEX data pipes: the two front ends have
-  // separate wavefront / writeback budgets (+10 %), and the constant cache takes the coherent top
-  // levels off both (+8 %; 5 levels and more lose to the serialisation of divergent constant loads).
-  // All-TEX is slower than all-LSU.  Measurements: profiles/README.md.
-  constexpr int kTex = 0xA;
-  const bool tex = f.tex != 0 && t.variant >= 0;
-  const int ctop = f.const_top_levels;  // 0 if the table does not hold this booster
-  if (a.pred_leaf) {
-    if (a.has_missing)
-      return tex ? launch_predict_one<4, true, true, true, 6, kTex>(f, a, s) : launch_predict_one<4, true, true, true, 6, 0>(f, a, s);
-    return tex ? launch_predict_one<4, false, true, true, 6, kTex>(f, a, s) : launch_predict_one<4, false, true, true, 6, 0>(f, a, s);
-  }
-  if (a.has_missing) {
-    if (tex && ctop == 4) return launch_predict_one<4, true, false, true, 6, kTex, 4>(f, a, s);
-    return tex ? launch_predict_one<4, true, false, true, 6, kTex>(f, a, s) : launch_predict_one<4, true, false, true, 6, 0>(f, a, s);
-  }
-  // clean matrix, sums: the production path.  Experiments (qcoh_set_param): park, ilp, minb, variant, top_levels, duo.
-  if (f.duo_ready) {  // the constant table holds this booster's heap-ordered tops (capi_xgb.cpp sync_const_top)
+  if (a.nrow == 0 || a.tree_end <= a.tree_begin) return cudaSuccess;
+  if (a.ncol > f.nfeat || f.nfeat > (int)kMaxFeatures) return cudaErrorInvalidValue;
+  const bool hm = a.has_missing != 0, pl = a.pred_leaf != 0;
+  const bool in_table = a.tree_begin >= f.const_tree0 && a.tree_end <= f.const_tree0 + f.const_ntree;
+  // ---- two-level records (the constant tables hold these trees' tops: capi_xgb.cpp sync_const_top)
+  if (f.duo_ready && in_table && (!hm || f.duo_has_dl)) {
+    g_last_predict = count_family("duo", hm, pl);
+    const bool persist = t.persist > 0 || (t.persist < 0 && f.sum_depth <= kShallowSumDepth);
+#ifdef QC_EXPERIMENTS
     // experiment grid (qcoh_set_param duo=1 + ilp / minb / duo_mask): trees in flight x resident CTAs x which
     // of the trees gather through the texture pipe; measurements in profiles/README.md
 #define QC_DUO(I, M, MASK) \
-  if (t.ilp == I && t.minb == M && t.duo_mask == MASK) return launch_predict_duo<I, M, MASK>(f, a, s);
+  if (t.ilp == I && t.minb == M && t.duo_mask == MASK) return launch_duo<I, M, MASK, 1>(f, a, 0, s);
     QC_DUO(4, 6, 0xA) QC_DUO(4, 6, 0xE) QC_DUO(4, 6, 0xF) QC_DUO(3, 6, 0x6) QC_DUO(3, 6, 0x2) QC_DUO(6, 5, 0x2A) QC_DUO(8, 4, 0xEE)
 #undef QC_DUO
-    return launch_predict_duo<kDuoIlp, kDuoMinBlocks, kDuoTexMask>(f, a, s);
+#endif
+    if (persist) return launch_duo<kDuoIlp, kPersistCtasPerSm, kDuoTexMask, 2>(f, a, kPersistCtasPerSm, s);
+    return launch_duo<kDuoIlp, kDuoMinBlocks, kDuoTexMask, 1>(f, a, 0, s);
   }
-  if (t.park == 0) return launch_predict_one<4, false, false, false, 6, 0>(f, a, s);
-  if (t.variant > 0 && f.tex) {
-#define QC_TEX(V, I, MASK)                                                                  \
-  if (t.variant == V)                                                                        \
-    return ctop == 4 ? launch_predict_one<I, false, false, true, 6, MASK, 4>(f, a, s)        \
-                     : launch_predict_one<I, false, false, true, 6, MASK, 0>(f, a, s);
-    QC_TEX(1, 4, 0xF) QC_TEX(2, 4, 0xA) QC_TEX(3, 4, 0x8) QC_TEX(4, 4, 0xE)
-    QC_TEX(5, 3, 0x4) QC_TEX(6, 3, 0x6) QC_TEX(7, 6, 0x2A) QC_TEX(8, 6, 0x24) QC_TEX(9, 8, 0xAA)
-    QC_TEX(10, 2, 0x2) QC_TEX(11, 5, 0x0A) QC_TEX(12, 5, 0x15)
+  // ---- 8-byte depth-ordered nodes: 4 trees in flight per thread; levels 0..3 of every tree from constant
+  // memory when the table holds them; below that, trees 1 and 3 of each group fetch their nodes through the
+  // texture pipe and trees 0 and 2 through the LSU (mask 0xA).  Measurements: profiles/README.md.
+  g_last_predict = count_family("nodes8", hm, pl);
+  constexpr int kTex = 0xA;
+  const bool tex = f.tex != 0 && t.variant >= 0;
+  const int ctop = in_table ? f.const_top_levels : 0;  // 0 if the table does not hold these trees
+#ifdef QC_EXPERIMENTS
+  if (!hm && !pl) {
+    if (t.park == 0) return launch_nodes8<4, false, 6, 0, 0>(f, a, s);
+    if (t.variant > 0 && f.tex) {
+#define QC_TEX(V, I, MASK) \
+  if (t.variant == V) return ctop == 4 ? launch_nodes8<I, true, 6, MASK, 4>(f, a, s) : launch_nodes8<I, true, 6, MASK, 0>(f, a, s);
+      QC_TEX(1, 4, 0xF) QC_TEX(2, 4, 0xA) QC_TEX(3, 4, 0x8) QC_TEX(4, 4, 0xE)
+      QC_TEX(5, 3, 0x4) QC_TEX(6, 3, 0x6) QC_TEX(7, 6, 0x2A) QC_TEX(8, 6, 0x24) QC_TEX(9, 8, 0xAA)
+      QC_TEX(10, 2, 0x2) QC_TEX(11, 5, 0x0A) QC_TEX(12, 5, 0x15)
 #undef QC_TEX
-  }
-  if (t.ilp > 0 || t.minb > 0 || !tex) {  // LSU-only builds
-    const int ilp = t.ilp > 0 ? t.ilp : 3, minb = t.minb > 0 ? t.minb : 6;
+    }
+    if (t.ilp > 0 || t.minb > 0) {  // LSU-only builds
+      const int ilp = t.ilp > 0 ? t.ilp : 3, minb = t.minb > 0 ? t.minb : 6;
 #define QC_CASE(I, M) \
-  if (ilp == I && minb == M) return launch_predict_one<I, false, false, true, M, 0>(f, a, s);
-    QC_CASE(1, 6) QC_CASE(2, 6) QC_CASE(3, 6) QC_CASE(4, 6) QC_CASE(6, 6)
-    QC_CASE(2, 5) QC_CASE(3, 5) QC_CASE(4, 5) QC_CASE(6, 5)
-    QC_CASE(2, 4) QC_CASE(3, 4) QC_CASE(4, 4) QC_CASE(6, 4) QC_CASE(8, 4)
-    QC_CASE(4, 3) QC_CASE(6, 3) QC_CASE(8, 3)
+  if (ilp == I && minb == M) return launch_nodes8<I, true, M, 0, 0>(f, a, s);
+      QC_CASE(1, 6) QC_CASE(2, 6) QC_CASE(3, 6) QC_CASE(4, 6) QC_CASE(6, 6)
+      QC_CASE(2, 5) QC_CASE(3, 5) QC_CASE(4, 5) QC_CASE(6, 5)
+      QC_CASE(2, 4) QC_CASE(3, 4) QC_CASE(4, 4) QC_CASE(6, 4) QC_CASE(8, 4)
+      QC_CASE(4, 3) QC_CASE(6, 3) QC_CASE(8, 3)
 #undef QC_CASE
-    return launch_predict_one<3, false, false, true, 6, 0>(f, a, s);
+    }
+    if (tex && (ctop == 3 || ctop == 5 || ctop == 6)) {
+      if (ctop == 3) return launch_nodes8<4, true, 6, kTex, 3>(f, a, s);
+      if (ctop == 5) return launch_nodes8<4, true, 6, kTex, 5>(f, a, s);
+      return launch_nodes8<4, true, 6, kTex, 6>(f, a, s);
+    }
   }
-  switch (ctop) {
-    case 3: return launch_predict_one<4, false, false, true, 6, kTex, 3>(f, a, s);
-    case 4: return launch_predict_one<4, false, false, true, 6, kTex, 4>(f, a, s);
-    case 5: return launch_predict_one<4, false, false, true, 6, kTex, 5>(f, a, s);
-    case 6: return launch_predict_one<4, false, false, true, 6, kTex, 6>(f, a, s);
-    default: return launch_predict_one<4, false, false, true, 6, kTex, 0>(f, a, s);
-  }
+#endif
+  if (!tex) return launch_nodes8<4, true, 6, 0, 0>(f, a, s);
+  if (ctop == 4) return launch_nodes8<4, true, 6, kTex, 4>(f, a, s);
+  return launch_nodes8<4, true, 6, kTex, 0>(f, a, s);
 }
 
 // =====================================================================================
@@ -703,23 +823,26 @@ cudaError_t launch_oh_state(const Run1Dev &r, cudaStream_t s) {
 // restarts at its first level and adds downward, so the DN sums are NOT a suffix scan: level k
 // needs its own forward chain x(k) + x(k+1) + ... (SURVEY.md hard part 6).  One thread per
 // column keeps KB chains per field in registers and sweeps the column once per block of KB
-// levels; the UP sums are a running prefix.  aod is kept in a scratch column (sums[5] is
-// reused as the aod buffer until the DN pass overwrites it level by level, top down, after
-// the level has been consumed by every chain that starts at or above it).
+// levels; the UP sums are a running prefix.  aod and PL_BST are kept (DIAG_AOD, DIAG_PL).
 constexpr int KB = 8;
-__global__ void __launch_bounds__(128) oh_sums_kernel(Run1Dev r, float *__restrict__ aod) {
+__global__ void __launch_bounds__(128) oh_sums_kernel(Run1Dev r) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= r.ncol) return;
   const int nc = r.ncol, km = r.km;
+  float *__restrict__ aod = r.aod;
   float *wdn = r.sums[0], *idn = r.sums[1], *iup = r.sums[2], *wup = r.sums[3], *aup = r.sums[4], *adn = r.sums[5];
   if (r.lat_deg) r.lat_deg[c] = __fmul_rn(r.LATS[c], r.r2d);         // latarr (:1444)
   if (r.so3) r.so3[c] = __fadd_rn(r.GMITO3[c], -r.GMITTO3[c]);       // stratO3 (:1446)
   // pass 1: aod and the UP prefixes
   float s_iup = 0.f, s_wup = 0.f, s_aup = 0.f;
   float z_up = r.ZLE_BST[c];
+  float p_up = r.PLE_BST[c];
   for (int k = 0; k < km; ++k) {
     const size_t e = (size_t)k * nc + c;
     const float z_dn = r.ZLE_BST[e + nc];
+    const float p_dn = r.PLE_BST[e + nc];
+    r.pl_bst[e] = __fmul_rn(__fadd_rn(p_up, p_dn), 0.5f);  // PL_BST (:1488): bb%PL, the DIAG_PL export (:1666)
+    p_up = p_dn;
     const float thick = __fadd_rn(z_up, -z_dn);  // REAL*8 gridBoxThickness holds this float exactly
     float sc = __fadd_rn(r.SCA[0][e], r.SCA[1][e]);
     sc = __fadd_rn(sc, r.SCA[2][e]);
@@ -763,8 +886,7 @@ __global__ void __launch_bounds__(128) oh_sums_kernel(Run1Dev r, float *__restri
 }
 
 cudaError_t launch_oh_sums(const Run1Dev &r, cudaStream_t s) {
-  // aod scratch: OH_boost is not written until oh_finalize, borrow it
-  oh_sums_kernel<<<(r.ncol + 127) / 128, 128, 0, s>>>(r, r.OH_boost);
+  oh_sums_kernel<<<(r.ncol + 127) / 128, 128, 0, s>>>(r);
   return QC_LAUNCHED();
 }
 

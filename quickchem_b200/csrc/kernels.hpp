@@ -16,25 +16,44 @@ struct DeviceForest {
   int const_top_levels = 0;              // levels of every tree currently held in the constant-memory table
   const uint4 *recs = nullptr;           // two-level records (forest.hpp DuoForest), or nullptr
   cudaTextureObject_t tex4 = 0;          // the records as a 1-D linear uint4 texture
-  int duo_ready = 0;                     // the constant-memory record-base table holds this booster
+  int duo_ready = 0;                     // the constant-memory tables hold trees [const_tree0, const_tree0 + const_ntree) of this booster's records
+  int duo_has_dl = 0;                    // the records carry the default-direction bits (DuoForest::has_default_bits)
+  uint32_t duo_blk_mul = 0;              // 1 << (32 - DuoForest::blk_shift): blk = mulhi(w3, duo_blk_mul)
+  int32_t const_tree0 = 0, const_ntree = 0;
   int32_t ntree = 0;
   int32_t nfeat = 0;
   int32_t max_depth = 0;
   int64_t num_nodes = 0;
+  int64_t sum_depth = 0;                 // sum over trees of the deepest leaf's depth (picks the launch shape)
   float base_score = 0.f;
 };
 
+// How many trees the constant-memory tables hold at once (4 levels x 16 entries per tree in 61 440 B).
+constexpr int kConstTreesMax = 480;
+
+// The device form of a DMatrix: order-preserving integer KEYS (kernels.cu) in feature-major tiles of 256 rows,
+// Xt[tile][col][256] — what a CTA's transposed shared-memory tile holds, so that a tile arrives with one bulk
+// async copy (TMA) and needs no staging arithmetic.  Missing entries (NaN or == missing) are key 0xFFFFFFFF.
+// Built by seal_tiles from the row-major float matrix, like libxgboost builds its SparsePage in
+// XGDMatrixCreateFromMat (OH_GridCompMod.F90:347).
+constexpr int kTileRows = 256;
+inline uint64_t tile_count(uint64_t nrow) { return (nrow + kTileRows - 1) / kTileRows; }
+inline size_t tile_words(uint64_t nrow, uint64_t ncol) { return (size_t)tile_count(nrow) * (size_t)ncol * kTileRows; }
+
 struct PredictArgs {
-  const float *X = nullptr;  // [nrow][ncol] row-major, device
+  const uint32_t *Xt = nullptr;  // key tiles, device
   uint64_t nrow = 0;
   int32_t ncol = 0;
-  float missing = 0.f;
   int has_missing = 1;       // 0: the sealed matrix holds no NaN / == missing entry
   int pred_leaf = 0;         // option_mask & 2
-  int32_t ntree_used = 0;
+  int32_t tree_begin = 0;    // this launch walks trees [tree_begin, tree_end) ...
+  int32_t tree_end = 0;
+  int32_t out_stride = 0;    // pred_leaf: floats per row in `out` (= trees used by the whole call)
+  int first = 1;             // sums: 1 = start from base_score, 0 = continue from the partial sum in out[row]
+  int last = 1;              // sums: 1 = apply the export transform, 0 = store the partial sum
   int exp10 = 0;             // fused export transform, OH_GridCompMod.F90:369,1569
   float scale = 1.f;
-  float *out = nullptr;      // device: [nrow] or [nrow][ntree_used]
+  float *out = nullptr;      // device: [nrow] or [nrow][out_stride]
 };
 
 struct Tunables {
@@ -46,20 +65,26 @@ struct Tunables {
   int minb = 0;      // min resident CTAs per SM the kernel is compiled for (register budget)
   int duo = -1;      // two-level records: -1 = default, 0 = off, 1 = on
   int duo_mask = 0;  // (experiment) texture-pipe tree mask of the two-level kernel, 0 = default
+  int persist = -1;  // persistent double-buffered tile loop: -1 = auto (shallow forests), 0 = off, 1 = on
 };
 
 constexpr bool kDuoDefault = true;  // two-level records by default when the booster qualifies
 
 uint64_t launch_count();
+// launches per kernel family since load, and the family that served the last predict launch
+// ("duo", "duo_missing", "duo_leaf", "duo_missing_leaf", "nodes8", "nodes8_missing", "nodes8_leaf", ...)
+uint64_t kernel_launches(const char *family);
+const char *last_predict_kernel();
 
 // (experiment) copy levels 0..levels-1 of every tree into the kernel's __constant__ table
 cudaError_t upload_const_top(const uint32_t *dev_nodes_xy, const uint32_t *tree_offset, int ntree, int levels, cudaStream_t s);
 // two-level layout: DuoForest::top_xy into the tree-top table and DuoForest::tree_slot into its base table
 cudaError_t upload_const_duo(const uint32_t *top_xy, const uint32_t *tree_slot, int ntree, cudaStream_t s);
 
-// flags[0] |= 1 if any entry is NaN or == missing; flags[0] |= 2 if any entry is +-inf
-// (and `missing` is finite) — what XGDMatrixCreateFromMat checks (xgboost src/data/data.cc).
-cudaError_t launch_scan_matrix(const float *X, uint64_t n, float missing, int *flags, cudaStream_t s);
+// Row-major float matrix -> key tiles.  flags[0] |= 1 if any entry is NaN or == missing; flags[0] |= 2 if any
+// entry is +-inf (and `missing` is finite) — what XGDMatrixCreateFromMat checks (xgboost src/data/data.cc).
+// X and Xt cover `nrow` rows starting at a tile boundary.
+cudaError_t launch_seal_tiles(const float *X, uint64_t nrow, int ncol, float missing, uint32_t *Xt, int *flags, cudaStream_t s);
 
 cudaError_t launch_predict(const DeviceForest &f, const PredictArgs &a, const Tunables &t, cudaStream_t s);
 
@@ -100,6 +125,7 @@ struct Run1Dev {
   float *PL_MOD, *NDWET;             // [km][ncol]
   float *sums[6];                    // wdn idn iup wup aup adn, [km][ncol]
   float *lat_deg, *so3;              // [ncol] latarr, stratO3 (written by oh_sums)
+  float *aod, *pl_bst;               // [km][ncol] aod (:1451-1466) and PL_BST (:1488), written by oh_sums
   float *OH_ML;                      // persistent [km][ncol]
   float *OH, *OH_boost;              // [km][ncol]
   float *LOSS_CH4, *LOSS_CO;         // optional [km][ncol] 1/s (build-defined)

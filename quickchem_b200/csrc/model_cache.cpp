@@ -80,6 +80,7 @@ Booster *cache_get(const std::string &fname) {
   b->version = ++g_version_counter;
   b->cache_owned = true;  // uploaded at first use (qcoh_oh_set_booster / predict), like qcoh_booster_parse
   Booster *raw = b.release();
+  g_live_handles.insert(raw);
   g_cache[fname] = raw;
   return raw;
 }
@@ -108,11 +109,15 @@ int qcoh_model_cache_size(void) { return (int)g_cache.size(); }
 
 int qcoh_model_cache_clear(void) {
   API_BEGIN
+  for (auto &kv : g_cache)
+    if (kv.second->oh_refs > 0)
+      throw Error("qcoh_model_cache_clear: the booster of '" + kv.first + "' is still used by a fused-Run1 handle (qcoh_oh_free first)");
   if (g.ready) CU(cudaStreamSynchronize(g.stream));
   for (auto &kv : g_cache) {
     Booster *b = kv.second;
     if (g_last_booster == b) g_last_booster = nullptr;
     b->magic = 0;
+    g_live_handles.erase(b);
     delete b;
   }
   g_cache.clear();

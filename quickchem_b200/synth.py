@@ -79,6 +79,9 @@ def _ar1(rng, shape, rho=0.95, nrow_len=None) -> np.ndarray:
     return out.reshape(shape)
 
 
+_LATLON_CACHE: dict = {}
+
+
 def raw_fields(n: int, seed: int | None = None, km: int = KM, rho: float = 0.95, col0: int = 0,
                ncol: int | None = None) -> Dict[str, np.ndarray]:
     """Synthetic import state for `OH_data_source = ONLINE_INST` on cubed sphere C<n>.
@@ -88,7 +91,10 @@ def raw_fields(n: int, seed: int | None = None, km: int = KM, rho: float = 0.95,
     columns, i.e. whole j-rows, so the AR(1) rows stay intact); seed it per rank.
     """
     rng = np.random.default_rng(20220726 + n if seed is None else seed)
-    lat, lon = cubed_sphere_latlon(n)
+    if n not in _LATLON_CACHE:
+        _LATLON_CACHE.clear()
+        _LATLON_CACHE[n] = cubed_sphere_latlon(n)
+    lat, lon = _LATLON_CACHE[n]
     if ncol is None:
         _, _, ncol = grid_dims(n)
         ncol -= col0
@@ -154,6 +160,32 @@ def raw_fields(n: int, seed: int | None = None, km: int = KM, rho: float = 0.95,
     f["oh_ALBUV"] = np.clip(0.46 + 0.25 * _ar1(rng, (ncol,), rho, n), 0.02, 0.9).astype(np.float32)
     f["TROPP"] = (10000.0 + 20000.0 * np.abs(np.sin(lat.astype(np.float64))) ** 1.5).astype(np.float32)
     return f
+
+
+def field_block_rows(n: int) -> int:
+    """j-rows per independently seeded block of `raw_fields_blocked`: 72 blocks per grid when 12 divides n."""
+    return n // 12 if n % 12 == 0 else 1
+
+
+def raw_fields_blocked(n: int, seed: int, j0: int = 0, j1: int | None = None, **kw) -> Dict[str, np.ndarray]:
+    """The synthetic state of j-rows [j0, j1) of C<n>, identical whatever the sharding: the (n, 6n) index space is
+    cut into blocks of `field_block_rows(n)` whole j-rows, block b is `raw_fields(..., seed = f(seed, b))` (there is
+    no correlation across j-rows, so blocks are independent), and a shard is the concatenation of the blocks it
+    covers.  1, 2, 4 or 8 ranks therefore see the very same global fields (bench.py checks the results across N)."""
+    jm = 6 * n
+    j1 = jm if j1 is None else j1
+    rows = field_block_rows(n)
+    assert j0 % rows == 0 and (j1 % rows == 0 or j1 == jm), "shards are whole blocks of j-rows"
+    if n not in _LATLON_CACHE:
+        _LATLON_CACHE.clear()
+        _LATLON_CACHE[n] = cubed_sphere_latlon(n)
+
+    def block(b):
+        r0, r1 = b * rows, min((b + 1) * rows, jm)
+        return raw_fields(n, seed=(seed * 1000003 + b) % (2**63), col0=r0 * n, ncol=(r1 - r0) * n, **kw)
+
+    parts = [block(b) for b in range(j0 // rows, (j1 + rows - 1) // rows)]
+    return {k: np.ascontiguousarray(np.concatenate([p[k] for p in parts], axis=-1)) for k in parts[0]}
 
 
 def noon_sza_deg(jday: int, lat: np.ndarray) -> np.ndarray:
@@ -323,6 +355,24 @@ def random_forest_structure(n_trees, max_depth, num_feature=NFEAT, seed=0, p_lea
         from .xgbmodel import tree_from_nested
         trees.append(tree_from_nested(spec(0)))
     return Forest(trees=trees, base_score=base_score, num_feature=num_feature)
+
+
+def replicate_forest(forest: Forest, times: int, jitter_rel: float = 1e-3, seed: int = 0) -> Forest:
+    """`times` copies of a grown forest back to back, each copy with its split thresholds jittered by a relative
+    N(0, jitter_rel) (so that the copies are distinct in memory and their walks differ a little) — a cheap stand-in for
+    a booster with `times` x as many grown trees (booster sweep: 500 and 1000 trees, forests larger than L2)."""
+    rng = np.random.default_rng(seed)
+    trees = []
+    for c in range(times):
+        for t in forest.trees:
+            cond = t.split_cond.copy()
+            if c > 0:
+                internal = t.left != -1
+                j = (1.0 + jitter_rel * rng.standard_normal(int(internal.sum()))).astype(np.float32)
+                cond[internal] = (cond[internal] * j).astype(np.float32)
+            trees.append(Tree(left=t.left, right=t.right, parent=t.parent, split_index=t.split_index, split_cond=cond,
+                              default_left=t.default_left, sum_hess=t.sum_hess))  # fmt: skip
+    return Forest(trees=trees, base_score=forest.base_score, num_feature=forest.num_feature)
 
 
 def prod_like_booster(n_trees=100, max_depth=18, n_sample=131072, min_leaf=8, seed=18, grid_n=48,

@@ -102,9 +102,11 @@ def tree_from_nested(spec) -> Tree:
         left.append(-1), right.append(-1), parent.append(p), sidx.append(0), cond.append(0.0), dl.append(0)
         return len(left) - 1
 
-    queue = [(new_node(-1), spec)]
+    from collections import deque
+
+    queue = deque([(new_node(-1), spec)])
     while queue:
-        nid, sp = queue.pop(0)
+        nid, sp = queue.popleft()
         if isinstance(sp, (int, float, np.floating)):
             cond[nid] = float(sp)
             continue
@@ -186,6 +188,41 @@ def legacy_binary_bytes(forest: Forest, with_binf: bool = True, objective: str |
 def write_legacy_binary(forest: Forest, path: str, with_binf: bool = True, objective: str | None = None) -> None:
     with open(path, "wb") as f:
         f.write(legacy_binary_bytes(forest, with_binf, objective))
+
+
+def read_legacy_binary(path: str) -> Forest:
+    """Inverse of `write_legacy_binary` for files this module wrote (tooling: the booster sweep replicates grown
+    forests; the library and the oracle have their own, stricter readers)."""
+    raw = open(path, "rb").read()
+    o = 4 if raw[:4] == b"binf" else 0
+    base_score, num_feature = struct.unpack_from("<fI", raw, o)
+    o += 136
+
+    def rstr():
+        nonlocal o
+        (n,) = struct.unpack_from("<Q", raw, o)
+        o += 8 + n
+        return raw[o - n : o].decode()
+
+    objective, booster = rstr(), rstr()
+    assert booster == "gbtree", booster
+    (num_trees,) = struct.unpack_from("<i", raw, o)
+    o += 160
+    trees = []
+    for _ in range(num_trees):
+        (n,) = struct.unpack_from("<i", raw, o + 4)
+        o += 148
+        nodes = np.frombuffer(raw, NODE_DTYPE, n, o)
+        o += 20 * n
+        st = np.frombuffer(raw, STAT_DTYPE, n, o)
+        o += 16 * n
+        par = nodes["parent"].astype(np.int64)
+        par = np.where(par == -1, -1, par & 0x7FFFFFFF)
+        trees.append(Tree(left=nodes["cleft"].astype(np.int32), right=nodes["cright"].astype(np.int32),
+                          parent=par.astype(np.int32), split_index=(nodes["sindex"] & 0x7FFFFFFF).astype(np.uint32),
+                          split_cond=nodes["info"].astype(np.float32), default_left=(nodes["sindex"] >> 31).astype(np.uint8),
+                          sum_hess=st["sum_hess"].astype(np.float32)))  # fmt: skip
+    return Forest(trees=trees, base_score=float(np.float32(base_score)), num_feature=int(num_feature), objective=objective)
 
 
 # --------------------------------------------------------------------------------------

@@ -267,16 +267,21 @@ def _key(v):
     return b ^ np.where(b >> 31, np.uint32(0xFFFFFFFF), np.uint32(0x80000000))
 
 
-def _duo_walk(rec, tslot, top, t, x, nfeat, max_depth):
+def _duo_walk(rec, tslot, top, t, x, nfeat, max_depth, blk_shift=18):
     """The device algorithm of walk_group_duo restated in numpy: 4 levels on the complete heap-ordered top,
-    then one 16-byte record per two levels.  Returns (leaf value bits, XGBoost node id) per row."""
+    then one 16-byte record per two levels; a missing entry (NaN) takes the default child (bit 0 of a top entry's
+    y word, bits 17 / 16 / 15 of w3 for root / left / right).  Returns (leaf value bits, XGBoost node id) per row."""
     n = len(x)
     ar = np.arange(n)
-    kx = np.concatenate([_key(x), np.zeros((n, 1), np.uint32)], axis=1).astype(np.uint64)  # slot nfeat: key 0
+    kx = np.concatenate([_key(np.nan_to_num(x)), np.zeros((n, 1), np.uint32)], axis=1).astype(np.uint64)  # slot nfeat: key 0
+    miss = np.concatenate([np.isnan(x), np.zeros((n, 1), bool)], axis=1)
     hi = np.ones(n, np.int64)
     for _ in range(4):
-        tx, tf = top[t, hi, 0].astype(np.uint64), (top[t, hi, 1] >> 26).astype(np.int64)
-        hi = 2 * hi + ((tx + kx[ar, tf]) >> 32).astype(np.int64)
+        tx, ty = top[t, hi, 0].astype(np.uint64), top[t, hi, 1].astype(np.int64)
+        tf = ty >> 26
+        right = ((tx + kx[ar, tf]) >> 32).astype(np.int64)
+        right = np.where(miss[ar, tf], 1 - (ty & 1), right)
+        hi = 2 * hi + right
     s = hi - 16 + int(tslot[t])
     walking = np.ones(n, bool)
     val, nid = np.zeros(n, np.uint32), np.zeros(n, np.uint32)
@@ -284,11 +289,15 @@ def _duo_walk(rec, tslot, top, t, x, nfeat, max_depth):
     while d <= max(max_depth, 3) + 1:
         r = rec[s]
         m = r[:, 3].astype(np.int64)
-        r1 = ((r[:, 0].astype(np.uint64) + kx[ar, m & 31]) >> 32).astype(np.int64)
+        f0 = m & 31
+        r1 = ((r[:, 0].astype(np.uint64) + kx[ar, f0]) >> 32).astype(np.int64)
+        r1 = np.where(miss[ar, f0], 1 - ((m >> 17) & 1), r1)
         xs = np.where(r1 == 1, r[:, 2], r[:, 1]).astype(np.uint64)
         ms = np.where(r1 == 1, m << 5, m)
-        r2 = ((xs + kx[ar, (ms >> 10) & 31]) >> 32).astype(np.int64)
-        blk = m >> 15
+        f1 = (ms >> 10) & 31
+        r2 = ((xs + kx[ar, f1]) >> 32).astype(np.int64)
+        r2 = np.where(miss[ar, f1], 1 - np.where(r1 == 1, (m >> 15) & 1, (m >> 16) & 1), r2)
+        blk = m >> blk_shift
         term = walking & (blk == 0)
         val, nid = np.where(term, r[:, 0], val), np.where(term, r[:, 1], nid)
         walking &= blk != 0
@@ -300,8 +309,8 @@ def _duo_walk(rec, tslot, top, t, x, nfeat, max_depth):
 
 def test_two_level_records_walk_like_the_flat_nodes(capi, tmp_path, small_forest):
     """forest.cpp::build_duo: the two-level record layout (complete heap-ordered tops with padded shallow
-    leaves + 16-byte records) must land every row in the same leaf as the depth-ordered 8-byte nodes — for grown
-    trees, stumps, single leaves and values exactly on thresholds."""
+    leaves + 16-byte records with default-direction bits) must land every row in the same leaf as the depth-ordered
+    8-byte nodes — for grown trees, stumps, single leaves, values exactly on thresholds and missing entries."""
     rng = np.random.default_rng(11)
     stumpy = xgbmodel.Forest(
         trees=[xgbmodel.tree_from_nested(1.5), xgbmodel.tree_from_nested((3, 0.5, True, -1.0, 2.0)),
@@ -320,6 +329,8 @@ def test_two_level_records_walk_like_the_flat_nodes(capi, tmp_path, small_forest
         b = capi.Booster(p, parse_only=True)
         nodes, off, depth, orig = b.flat()
         rec, tslot, top = b.duo()
+        blk_shift, has_dl = b.duo_info()
+        assert (blk_shift, has_dl) == (18, True)  # none of these trees needs 2^14 record blocks
         assert rec.shape[1] == 4 and np.all(tslot % 8 == 0)  # tree bases on 128-byte lines
         nf = forest.num_feature
         x = rng.normal(0, 1, (3000, nf)).astype(np.float32)
@@ -327,15 +338,19 @@ def test_two_level_records_walk_like_the_flat_nodes(capi, tmp_path, small_forest
         internal = np.nonzero(nodes[:, 1] & ((1 << 23) - 1))[0]
         for i in rng.choice(internal, min(len(internal), 300), replace=False) if len(internal) else ():  # on thresholds
             x[rng.integers(len(x)), int(nodes[i, 1] >> 26)] = thr[i]
+        x[1500:][rng.random((1500, nf)) < 0.08] = np.nan  # the second half has missing entries
         xs = np.concatenate([x, np.full((len(x), 1), -np.inf, np.float32)], axis=1)
         feat, rel = (nodes[:, 1] >> 26).astype(np.int64), (nodes[:, 1] & ((1 << 23) - 1)).astype(np.int64)
+        dleft = ((nodes[:, 1] >> 23) & 1).astype(bool)
         ar = np.arange(len(x))
         for t in range(len(off) - 1):
             idx = np.full(len(x), off[t], np.int64)
             for _ in range(int(depth[t]) + 1):
-                right = ~(xs[ar, feat[idx]] < thr[idx])
+                v = xs[ar, feat[idx]]
+                with np.errstate(invalid="ignore"):
+                    right = np.where(np.isnan(v), ~dleft[idx], ~(v < thr[idx]))
                 idx = np.where(rel[idx] != 0, idx + rel[idx] + right, idx)
-            val, nid = _duo_walk(rec, tslot, top, t, x, nf, int(depth[t]))
+            val, nid = _duo_walk(rec, tslot, top, t, x, nf, int(depth[t]), blk_shift)
             assert np.array_equal(val, nodes[idx, 0]), (name, t)
             assert np.array_equal(nid, orig[idx].astype(np.uint32)), (name, t)
 
