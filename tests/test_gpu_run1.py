@@ -99,6 +99,15 @@ def test_diag_exports(capi, oracle, small_model_path):
     assert np.array_equal(oh.get_diag("NDWET"), got["NDWET"]) and np.array_equal(oh.get_diag("OH_boost"), got["OH_boost"])
     with pytest.raises(capi.QcohError, match="unknown"):
         oh.get_diag("nope")
+    # the noon-SZA cache follows the CONTENTS of LATS / LONS, not only their addresses (a host that re-uses its buffers)
+    sza0 = oh.get_diag("SZA")
+    f2 = dict(fields)
+    f2["LATS"] = fields["LATS"]
+    fields["LATS"][:] = (fields["LATS"] * np.float32(0.5)).astype(np.float32)  # same buffer, new grid
+    oh.run(oh.make_in(f2), want=("OH",))
+    ref2 = oracle.run1(oracle.Model(small_model_path), f2, synth.MAPL, want_features=True)
+    assert not np.array_equal(oh.get_diag("SZA"), sza0)
+    assert np.array_equal(oh.get_diag("SZA").view(np.uint32), ref2["feat"][26].view(np.uint32))
 
 
 def test_run1_dynamic_k_range(capi, oracle, small_model_path):
@@ -111,8 +120,17 @@ def test_run1_distinct_model_state(capi, oracle, small_model_path):
     """ONLINE_AVG24 / PRECOMPUTED: model-state T/Q/PLE differ from the boost-state ones."""
     fields = synth.raw_fields(8)
     mod = synth.raw_fields(8, seed=99)
-    got, ref, _, _ = _run_both(capi, oracle, small_model_path, fields, mod_fields=mod)
+    got, ref, oh, _ = _run_both(capi, oracle, small_model_path, fields, mod_fields=mod)
     _assert_parity(got, ref)
+    # DIAG_PL is bb%PL = PL_BST (from the PLE handed to boost, :1488,:1666), not the model state's PL_MOD; DIAG_AOD (:1690)
+    pl_bst = ((fields["PLE"][:-1] + fields["PLE"][1:]) * np.float32(0.5)).astype(np.float32)
+    pl_mod = ((mod["PLE"][:-1] + mod["PLE"][1:]) * np.float32(0.5)).astype(np.float32)
+    assert np.array_equal(oh.get_diag("PL"), pl_bst) and np.array_equal(oh.get_diag("PL_MOD"), pl_mod)
+    assert not np.array_equal(pl_bst, pl_mod)
+    assert np.array_equal(oh.get_diag("PL").reshape(-1) / np.float32(100.0), ref["X"][:, 1]) or got["k1"] > 1
+    sca = sum(fields[s + "SCACOEF"] for s in synth.SCA_SPECIES[1:])
+    assert oh.get_diag("AOD").shape == fields["T"].shape
+    assert np.array_equal(np.cumsum(oh.get_diag("AOD"), axis=0, dtype=np.float32)[0], oh.get_diag("AODUP")[0]) and sca.shape == fields["T"].shape
 
 
 def test_run1_tropopause_assert(capi, oracle, small_model_path):

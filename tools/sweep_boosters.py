@@ -6,6 +6,8 @@
     the 100-tree booster of that depth replicated 5 x / 10 x with jittered thresholds (synth.replicate_forest);
 (b) forests larger than the 126 MB L2: a 20-tree booster with ~1e5 nodes per tree (grown on 700 k samples,
     min_leaf 2) replicated to 100 trees; both node layouts are timed (`duo` = 0 / 1);
+(d) the production-shape booster on a matrix with 1 % missing entries (-999.0): the same two-level kernel with the
+    default-direction test, against the clean matrix;
 (c) one model day of 24 hourly steps with compute_once_per_day (1 boost step + 23 steps that reuse the persistent
     OH_ML), fields resident in HBM.
     python tools/sweep_boosters.py [--grid 180] [--grow-only] [--part a,b,c] [--persist -1]"""
@@ -27,7 +29,7 @@ ap.add_argument("--grid", type=int, default=180)
 ap.add_argument("--grow-only", action="store_true")
 ap.add_argument("--trees", default="10,30,100,500,1000")
 ap.add_argument("--depths", default="6,10,14,18")
-ap.add_argument("--part", default="a,b,c")
+ap.add_argument("--part", default="a,b,d,c")
 ap.add_argument("--persist", default="-1", help="comma list of qcoh_set_param persist values to time (sweep a)")
 ap.add_argument("--iters", type=int, default=10)
 a = ap.parse_args()
@@ -148,7 +150,7 @@ if "a" in parts:
 
 if "b" in parts:
     seed = xgbmodel.read_legacy_binary(big_seed_path())
-    for times in (1, 5):
+    for times in (1, 7):
         f = synth.replicate_forest(seed, times, seed=99)
         p = os.path.join(tmp, f"big_{times}.model")
         xgbmodel.write_legacy_binary(f, p)
@@ -161,6 +163,27 @@ if "b" in parts:
             row(b, dX, hx, ms, sweep="forest vs L2 (126 MB)", duo=duo, nodes_per_tree=int(b.info().num_nodes // b.info().num_trees))
         capi.set_param("duo", -1)
         b.free()
+
+if "d" in parts:
+    b = capi.Booster(grown_path(100, 18))
+    dX, hx = matrix(b)
+    ms_clean = time_predict(b, dX)
+    row(b, dX, hx, ms_clean, sweep="missing entries", missing_frac=0.0)
+    xp = capi.vp()
+    capi.check(capi.lib().qcoh_dmatrix_device_ptr(dX.handle, capi.C.byref(xp)))
+    full = np.empty((ncell, 27), np.float32)
+    capi.check(capi.lib().qcoh_memcpy_d2h(full.ctypes.data_as(capi.vp), xp, full.nbytes))
+    rng = np.random.default_rng(4)
+    idx = rng.integers(0, full.size, full.size // 100)
+    full.reshape(-1)[idx] = np.float32(-999.0)
+    dM = capi.DMatrix.device(ncell, 27)
+    dM.upload(full)
+    dM.seal()
+    ms_miss = time_predict(b, dM)
+    row(b, dM, hx, ms_miss, sweep="missing entries", missing_frac=0.01, slowdown=round(ms_miss / ms_clean, 4))
+    dM.free()
+    del full
+    b.free()
 
 if "c" in parts:
     # one model day: 24 hourly steps, compute_once_per_day
