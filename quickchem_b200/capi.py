@@ -15,7 +15,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libqcoh.so")
+LIB_PATH = os.environ.get("QCOH_LIB") or os.path.join(_HERE, "libqcoh.so")  # QCOH_LIB: the experiment build
 
 f32p = C.POINTER(C.c_float)
 u64 = C.c_uint64
@@ -396,7 +396,7 @@ class Booster:
         out = np.ctypeslib.as_array(p, (n.value,)).copy() if n.value else np.zeros(0, np.float32)
         if option_mask & 2:
             nt = self.info().num_trees if ntree_limit == 0 else min(ntree_limit, self.info().num_trees)
-            out = out.reshape(-1, nt)
+            out = out.reshape(-1, nt) if nt else np.zeros((dmat.num_row, 0), np.float32)
         return out
 
     def predict_raw(self, dmat: DMatrix, option_mask=0, ntree_limit=0):

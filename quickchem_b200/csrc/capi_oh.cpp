@@ -81,7 +81,7 @@ struct Oh {
 constexpr int kProbe = 2048;
 // FNV-1a over a strided sample of both coordinate arrays (host or device memory)
 uint64_t grid_probe_hash(Oh *o, const float *lat, const float *lon, size_t n) {
-  const size_t stride = std::max<size_t>(1, n / kProbe), cnt = std::min<size_t>(n, (n + stride - 1) / stride);
+  const size_t stride = (n + kProbe - 1) / kProbe, cnt = (n + stride - 1) / stride;  // cnt <= kProbe
   float *h = o->h_probe.need(2 * (size_t)kProbe + 2);
   CU(cudaMemcpy2DAsync(h, sizeof(float), lat, stride * sizeof(float), sizeof(float), cnt, cudaMemcpyDefault, g.stream));
   CU(cudaMemcpy2DAsync(h + cnt, sizeof(float), lon, stride * sizeof(float), sizeof(float), cnt, cudaMemcpyDefault, g.stream));

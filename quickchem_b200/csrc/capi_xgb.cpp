@@ -8,6 +8,9 @@
 #ifdef __linux__
 #include <sched.h>
 #endif
+#if defined(__x86_64__)
+#include <emmintrin.h>
+#endif
 
 using namespace qcoh;
 
@@ -89,14 +92,15 @@ void upload(Booster *b) {
   b->uploaded = true;
 }
 
-// The constant-memory tables of tree tops are one per process (one __constant__ bank per loaded module): they
-// hold one range of <= kConstTreesMax trees of one booster at a time, in one of two layouts — the first levels
+// The constant-memory tables of tree tops exist once per device (one __constant__ bank per loaded module and
+// device), and a device is driven by exactly one host thread (context.hpp): they hold one range of
+// <= kConstTreesMax trees of one booster at a time, in one of two layouts — the first levels
 // of the depth-ordered nodes (walk_group), or the complete heap-ordered tops of the two-level records
-// (walk_group_duo).  The owner tag below is therefore process-wide by construction; everything else a launch
-// needs travels in the booster's DeviceForest.  allow_duo = false forces the 8-byte-node layout.
-static uint64_t g_const_top_owner = 0;
-static int g_const_top_levels = 0;  // kConstDuo = two-level layout
-static int g_const_tree0 = 0, g_const_ntree = 0;
+// (walk_group_duo).  The owner tag below is therefore per device = per thread; everything else a launch needs
+// travels in the booster's DeviceForest.  allow_duo = false forces the 8-byte-node layout.
+static thread_local uint64_t g_const_top_owner = 0;
+static thread_local int g_const_top_levels = 0;  // kConstDuo = two-level layout
+static thread_local int g_const_tree0 = 0, g_const_ntree = 0;
 constexpr int kConstDuo = -1;
 bool duo_wanted(const Booster *b) {
   if (b->dev.recs == nullptr || b->dev.tex == 0 || g.tun.duo == 0) return false;
@@ -230,6 +234,31 @@ static bool is_pinned_host(const void *p) {
 // memory (xx_carr, OH_GridCompMod.F90:306), and one core's memcpy (~10 GB/s) is far below PCIe 5 x16.  The
 // workers are created once and parked on a condition variable; spawning threads per chunk cost more than the copy
 // of a small chunk.  Threads: the cores this process may use divided by the ranks sharing the node.
+// Copy into the pinned staging ring with non-temporal stores: a plain memcpy reads every destination line before
+// overwriting it (read-for-ownership), i.e. 3 transfers per byte where the staging copy needs 2, and the staging
+// data is only ever read back by the DMA engine.  QCOH_COPY_NT=0 selects memcpy.
+static void stream_copy(char *dst, const char *src, size_t n) {
+  size_t i = 0;
+#if defined(__x86_64__)
+  static const bool nt = [] {
+    const char *e = getenv("QCOH_COPY_NT");
+    return !e || atoi(e) != 0;
+  }();
+  if (nt && (((uintptr_t)dst) & 15u) == 0u) {
+    for (; i + 64 <= n; i += 64) {
+      const __m128i a = _mm_loadu_si128((const __m128i *)(src + i)), b = _mm_loadu_si128((const __m128i *)(src + i + 16));
+      const __m128i c = _mm_loadu_si128((const __m128i *)(src + i + 32)), d = _mm_loadu_si128((const __m128i *)(src + i + 48));
+      _mm_stream_si128((__m128i *)(dst + i), a);
+      _mm_stream_si128((__m128i *)(dst + i + 16), b);
+      _mm_stream_si128((__m128i *)(dst + i + 32), c);
+      _mm_stream_si128((__m128i *)(dst + i + 48), d);
+    }
+    _mm_sfence();
+  }
+#endif
+  if (i < n) memcpy(dst + i, src + i, n - i);
+}
+
 class CopyPool {
  public:
   static CopyPool &get() {
@@ -237,9 +266,10 @@ class CopyPool {
     return p;
   }
   void copy(void *dst, const void *src, size_t bytes) {
+    std::lock_guard<std::mutex> one_caller(callers_);  // threads driving different GPUs share the workers
     const unsigned nt = (unsigned)workers_.size() + 1;
     if (nt == 1 || bytes < ((size_t)4 << 20)) {
-      memcpy(dst, src, bytes);
+      stream_copy((char *)dst, (const char *)src, bytes);
       return;
     }
     const size_t per = (bytes / nt + 4095) / 4096 * 4096;
@@ -280,7 +310,7 @@ class CopyPool {
   }
   void part(unsigned t) {
     const size_t o = (size_t)t * per_;
-    if (o < bytes_) memcpy(dst_ + o, src_ + o, std::min(per_, bytes_ - o));
+    if (o < bytes_) stream_copy(dst_ + o, src_ + o, std::min(per_, bytes_ - o));
   }
   void run(unsigned t) {
     uint64_t seen = 0;
@@ -297,7 +327,7 @@ class CopyPool {
     }
   }
   std::vector<std::thread> workers_;
-  std::mutex m_;
+  std::mutex m_, callers_;
   std::condition_variable cv_, done_;
   char *dst_ = nullptr;
   const char *src_ = nullptr;
@@ -309,8 +339,8 @@ class CopyPool {
 static void parallel_memcpy(void *dst, const void *src, size_t bytes) { CopyPool::get().copy(dst, src, bytes); }
 
 constexpr int kStageSlots = 3;
-static PinBuf<float> g_stage[kStageSlots];
-static cudaEvent_t g_stage_free[kStageSlots] = {nullptr, nullptr, nullptr};
+static thread_local PinBuf<float> g_stage[kStageSlots];
+static thread_local cudaEvent_t g_stage_free[kStageSlots] = {nullptr, nullptr, nullptr};
 
 // XGDMatrixCreateFromMat from HOST memory, pipelined: the matrix is cut into row chunks; while chunk
 // c+1 crosses PCIe, chunk c is scanned (missing / inf) and — since the reference keeps exactly one
@@ -406,6 +436,7 @@ static void create_pipelined(DMatrix *d, const float *data, Booster *b) {
 extern "C" {
 
 const char *XGBGetLastError(void) { return g_err.c_str(); }
+__attribute__((visibility("hidden"))) void qcoh_internal_set_error(const char *msg) { g_err = msg ? msg : ""; }
 
 int XGBoosterCreate(const DMatrixHandle dmats[], bst_ulong len, BoosterHandle *out) {
   API_BEGIN

@@ -21,17 +21,21 @@ typedef int ncclResult_t;     // ncclSuccess == 0
 constexpr int kNcclFloat64 = 8;  // ncclDouble
 constexpr int kNcclSum = 0;      // ncclSum
 
-struct Nccl {
+struct NcclApi {
   void *lib = nullptr;
   ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
   ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
   ncclResult_t (*AllReduce)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
   const char *(*GetErrorString)(ncclResult_t) = nullptr;
+};
+// the dlopen'ed entry points are process-wide; the communicator belongs to the calling thread's rank
+struct Nccl : NcclApi {
   ncclComm_t comm = nullptr;
   int nranks = 0, rank = -1;
   DevBuf<double> buf;
-} nccl;
+};
+thread_local Nccl nccl;
 
 void load_nccl() {
   if (nccl.lib) return;

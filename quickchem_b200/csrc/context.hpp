@@ -10,6 +10,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <memory>
+#include <mutex>
 #include <stdexcept>
 #include <string>
 #include <thread>
@@ -58,6 +59,12 @@ struct NvtxRange {
   return 0;
 
 // ---- device context ---------------------------------------------------------------
+// Thread model ("one process per GPU" and "one process, one host thread per device" are both
+// supported): ALL mutable library state — the device context below, the buffer pools, the constant-table owner
+// tag, the live-handle set, the model cache, the mirror's SAVE'd booster, the NCCL communicator — is
+// thread_local.  A host thread is one "rank": it binds to one GPU (qcoh_set_device / $LOCAL_RANK) and owns the
+// handles it creates; a handle is not valid in another thread.  One thread per device: the constant-memory tables
+// are per device, so a second thread binding to a device that already has an owner is refused.
 struct Ctx {
   bool ready = false;
   int device = -1;
@@ -72,9 +79,24 @@ struct Ctx {
   size_t flush_bytes = 0;
   Tunables tun;
 };
-inline Ctx g;
+inline thread_local Ctx g;
 
-inline int requested_device = -1;
+inline thread_local int requested_device = -1;
+
+// device -> the thread that owns it (process-wide; the only shared mutable state besides the copy pool)
+inline std::mutex g_device_owner_mutex;
+inline std::thread::id g_device_owner[64];
+inline bool g_device_owned[64] = {false};
+struct DeviceLease {  // released when the owning thread ends
+  int device = -1;
+  ~DeviceLease() {
+    if (device >= 0) {
+      std::lock_guard<std::mutex> lk(g_device_owner_mutex);
+      g_device_owned[device] = false;
+    }
+  }
+};
+inline thread_local DeviceLease g_device_lease;
 
 inline void ensure_device() {
   if (g.ready) return;
@@ -91,6 +113,13 @@ inline void ensure_device() {
     dev = lr ? atoi(lr) % n : 0;
   }
   if (dev >= n) throw Error("libqcoh: device " + std::to_string(dev) + " requested but only " + std::to_string(n) + " visible");
+  if (dev < 64) {
+    std::lock_guard<std::mutex> lk(g_device_owner_mutex);
+    if (g_device_owned[dev] && g_device_owner[dev] != std::this_thread::get_id())
+      throw Error("libqcoh: device " + std::to_string(dev) + " is already driven by another host thread of this process (one thread per GPU)");
+    g_device_owned[dev] = true, g_device_owner[dev] = std::this_thread::get_id();
+    g_device_lease.device = dev;
+  }
   CU(cudaSetDevice(dev));
   cudaDeviceProp p;
   CU(cudaGetDeviceProperties(&p, dev));
@@ -174,7 +203,7 @@ constexpr uint32_t kDMatrixMagic = 0x5143444d;  // 'QCDM'
 constexpr uint32_t kOhMagic = 0x51434f48;       // 'QCOH'
 
 // Live handles: a freed handle is recognised by its absence here, not by reading freed memory.
-inline std::unordered_set<const void *> g_live_handles;
+inline thread_local std::unordered_set<const void *> g_live_handles;
 inline bool is_live(const void *h) { return h && g_live_handles.count(h) != 0; }
 
 struct Booster {
@@ -223,14 +252,14 @@ struct DMatrix {
 // XGDMatrixFree keeps the largest freed matrix buffer for the next XGDMatrixCreateFromMat: the
 // reference creates and frees a same-sized DMatrix on every call (OH_GridCompMod.F90:347,377) and
 // cudaMalloc / cudaFree of multi-GB buffers would otherwise dominate the step.
-inline DevBuf<float> g_spare_X;
-inline DevBuf<uint32_t> g_spare_Xt;
-inline PinBuf<float> g_spare_pin;
-inline DevBuf<float> g_spare_spec;
-inline DevBuf<int> g_chunk_flags;
-inline PinBuf<int> g_h_chunk_flags;
-inline Booster *g_last_booster = nullptr;  // the process's booster (the reference keeps exactly one, SAVE :182)
-inline uint64_t g_version_counter = 0;
+inline thread_local DevBuf<float> g_spare_X;
+inline thread_local DevBuf<uint32_t> g_spare_Xt;
+inline thread_local PinBuf<float> g_spare_pin;
+inline thread_local DevBuf<float> g_spare_spec;
+inline thread_local DevBuf<int> g_chunk_flags;
+inline thread_local PinBuf<int> g_h_chunk_flags;
+inline thread_local Booster *g_last_booster = nullptr;  // the process's booster (the reference keeps exactly one, SAVE :182)
+inline thread_local uint64_t g_version_counter = 0;
 
 inline Booster *B(BoosterHandle h) {
   Booster *b = (Booster *)h;

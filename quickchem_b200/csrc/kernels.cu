@@ -22,12 +22,13 @@
 #include <cfloat>
 #include <cmath>
 #include <cstring>
+#include <vector>
 
 #include "forest.hpp"
 
 namespace qcoh {
 
-static uint64_t g_launches = 0;
+static thread_local uint64_t g_launches = 0;
 uint64_t launch_count() { return g_launches; }
 
 #define QC_LAUNCHED() (++g_launches, cudaGetLastError())
@@ -38,9 +39,9 @@ struct FamilyCount {
   char name[32];
   uint64_t n;
 };
-FamilyCount g_family[24];
-int g_nfamily = 0;
-const char *g_last_predict = "";
+thread_local FamilyCount g_family[24];
+thread_local int g_nfamily = 0;
+thread_local const char *g_last_predict = "";
 const char *count_family(const char *base, bool hm, bool pl) {
   char name[32];
   snprintf(name, sizeof name, "%s%s%s", base, hm ? "_missing" : "", pl ? "_leaf" : "");
@@ -129,7 +130,7 @@ __constant__ uint32_t c_duo_base[kConstTreesMax];
 cudaError_t upload_const_top(const uint32_t *dev_nodes_xy, const uint32_t *tree_offset, int ntree, int levels, cudaStream_t s) {
   const int stride = 1 << levels;
   if (levels <= 0 || (int64_t)ntree * stride > kConstTopNodes) return cudaErrorInvalidValue;
-  static uint2 host[kConstTopNodes];
+  std::vector<uint2> host((size_t)ntree * stride);
   for (int t = 0; t < ntree; ++t) {
     const uint32_t n0 = tree_offset[t], n1 = tree_offset[t + 1];
     for (int i = 0; i < stride; ++i) {
@@ -137,7 +138,8 @@ cudaError_t upload_const_top(const uint32_t *dev_nodes_xy, const uint32_t *tree_
       host[t * stride + i] = n < n1 ? make_uint2(dev_nodes_xy[2 * n], dev_nodes_xy[2 * n + 1]) : make_uint2(0u, 0u);
     }
   }
-  return cudaMemcpyToSymbolAsync(c_top, host, sizeof(uint2) * (size_t)ntree * stride, 0, cudaMemcpyHostToDevice, s);
+  // pageable source: the call returns once the data is staged, so the local buffer may go
+  return cudaMemcpyToSymbolAsync(c_top, host.data(), sizeof(uint2) * (size_t)ntree * stride, 0, cudaMemcpyHostToDevice, s);
 }
 
 cudaError_t upload_const_duo(const uint32_t *top_xy, const uint32_t *tree_slot, int ntree, cudaStream_t s) {
@@ -671,7 +673,7 @@ cudaError_t launch_predict_soa(const DeviceForest &f, const SoaArgs &a, const Tu
 }
 
 // ---- launches ------------------------------------------------------------------------------------------
-static int g_sm_count = 0;
+static thread_local int g_sm_count = 0;
 static int sm_count() {
   if (g_sm_count == 0) {
     int dev = 0;
@@ -713,11 +715,9 @@ static cudaError_t launch_nodes8(const DeviceForest &f, const PredictArgs &a, cu
   return launch_tiles(predict_tiles_nodes8_kernel<ILP, false, false, PARK, MINB, TEXMODE, CTOP>, f, a, 1, 0, s);
 }
 
-// A forest is "shallow" when a row's walk is short enough for the tile stream to matter (the HBM-bound end of the
-// booster sweep, profiles/): those launches run persistent with a double-buffered TMA prefetch.
-// Two 28 KB buffers per CTA: three CTAs per SM (four would need 64 bytes more than the SM's 228 KB once the 1 KB
+// Persistent double-buffered variant (TMA prefetch of the next tile while this one is walked), for the HBM-bound
+// end of the booster sweep.  Two 28 KB buffers per CTA: three CTAs per SM (four would need 64 bytes more than the SM's 228 KB once the 1 KB
 // the system reserves per CTA is counted).
-constexpr int64_t kShallowSumDepth = 400;
 constexpr int kPersistCtasPerSm = 3;
 
 cudaError_t launch_predict(const DeviceForest &f, const PredictArgs &a, const Tunables &t, cudaStream_t s) {
@@ -728,13 +728,18 @@ cudaError_t launch_predict(const DeviceForest &f, const PredictArgs &a, const Tu
   // ---- two-level records (the constant tables hold these trees' tops: capi_xgb.cpp sync_const_top)
   if (f.duo_ready && in_table && (!hm || f.duo_has_dl)) {
     g_last_predict = count_family("duo", hm, pl);
-    const bool persist = t.persist > 0 || (t.persist < 0 && f.sum_depth <= kShallowSumDepth);
+    // measured (profiles/README.md): with two 28 KB buffers only three CTAs fit an SM, and the lost residency costs
+    // more than the prefetch wins — the persistent loop is opt-in (qcoh_set_param persist=1), not the default
+    const bool persist = t.persist > 0;
 #ifdef QC_EXPERIMENTS
     // experiment grid (qcoh_set_param duo=1 + ilp / minb / duo_mask): trees in flight x resident CTAs x which
     // of the trees gather through the texture pipe; measurements in profiles/README.md
 #define QC_DUO(I, M, MASK) \
   if (t.ilp == I && t.minb == M && t.duo_mask == MASK) return launch_duo<I, M, MASK, 1>(f, a, 0, s);
     QC_DUO(4, 6, 0xA) QC_DUO(4, 6, 0xE) QC_DUO(4, 6, 0xF) QC_DUO(3, 6, 0x6) QC_DUO(3, 6, 0x2) QC_DUO(6, 5, 0x2A) QC_DUO(8, 4, 0xEE)
+    // shallow forests (the HBM-bound end): more resident CTAs, fewer trees in flight, LSU-only gathers
+    QC_DUO(4, 6, 0x100) QC_DUO(3, 6, 0x100) QC_DUO(2, 6, 0x100) QC_DUO(2, 6, 0x2) QC_DUO(6, 5, 0x100) QC_DUO(6, 5, 0x14)
+    QC_DUO(4, 7, 0x100) QC_DUO(4, 7, 0xA) QC_DUO(3, 7, 0x100) QC_DUO(3, 7, 0x2) QC_DUO(2, 7, 0x100) QC_DUO(5, 6, 0x100) QC_DUO(5, 6, 0xA)
 #undef QC_DUO
 #endif
     if (persist) return launch_duo<kDuoIlp, kPersistCtasPerSm, kDuoTexMask, 2>(f, a, kPersistCtasPerSm, s);

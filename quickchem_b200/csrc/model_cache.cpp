@@ -12,7 +12,7 @@ using namespace qcoh;
 namespace {
 
 // keyed by the file name as given (after template expansion); owns the boosters
-std::map<std::string, Booster *> g_cache;
+thread_local std::map<std::string, Booster *> g_cache;  // per host thread = per GPU (context.hpp)
 
 void put2(std::string &o, int v, int width) {
   char buf[16];

@@ -17,16 +17,23 @@
 namespace {
 
 // SAVE variables of the reference (OH_GridCompMod.F90:182,209): one booster per process
-BoosterHandle xx_bst = nullptr;
-bool first_time = true;
+// (thread_local: a host thread is one rank bound to one GPU, see context.hpp)
+thread_local BoosterHandle xx_bst = nullptr;
+thread_local bool first_time = true;
 // opt-in fix of SURVEY.md 0.5 (the file name carries the month but the booster is loaded once)
-bool reload_on_file_change = false;
-std::string loaded_fname;
+thread_local bool reload_on_file_change = false;
+thread_local std::string loaded_fname;
 
 constexpr int64_t xx_param_count = 27;  // :228
 constexpr float xx_miss = -999.0f;      // :213
 
-thread_local std::string mirror_err;
+}  // namespace
+
+// the library's last-error string (XGBGetLastError's), for the messages of the reference's own _ASSERTs;
+// internal to libqcoh.so (hidden), defined in capi_xgb.cpp
+extern "C" __attribute__((visibility("hidden"))) void qcoh_internal_set_error(const char *msg);
+
+namespace {
 
 template <class F>
 void parallel_for(int64_t n, F &&body) {
@@ -70,9 +77,19 @@ extern "C" int qcoh_predict_OH_with_XGB(const char *xgb_fname, int icount, int j
     if (rc != 0) return -1;  // _ASSERT 'Failed in XGDMatrixCreateFromMat_f'
     // the reference hands the DMatrix handle itself as `dmats` with len = 0 (:255-256)
     rc = XGBoosterCreate((const DMatrixHandle *)xx_dmtrx, 0, &xx_bst);
-    if (rc != 0) return -1;
+    if (rc != 0) {
+      XGDMatrixFree(xx_dmtrx);
+      return -1;
+    }
     rc = XGBoosterLoadModel(xx_bst, xgb_fname);
-    if (rc != 0) return -1;
+    if (rc != 0) {  // a retry must not leak this pair (first_time stays true); keep the loader's message
+      const std::string why = XGBGetLastError();
+      XGDMatrixFree(xx_dmtrx);
+      XGBoosterFree(xx_bst);
+      xx_bst = nullptr;
+      qcoh_internal_set_error(why.c_str());
+      return -1;
+    }
     rc = XGDMatrixFree(xx_dmtrx);
     if (rc != 0) return -1;
     first_time = false;
@@ -88,7 +105,10 @@ extern "C" int qcoh_predict_OH_with_XGB(const char *xgb_fname, int icount, int j
   int ksubcount = 0;
   if (!dynamic_k_range) {
     for (int64_t c = 0; c < ncol; ++c)
-      if (tropp[c] <= tropp_min) return -1;  // _ASSERT 'Minimum tropopause pressure is not low enough!'
+      if (tropp[c] <= tropp_min) {  // _ASSERT(ALL(tropp > tropp_min), ...) (:287-288)
+        qcoh_internal_set_error("OH Prediction: Minimum tropopause pressure is not low enough!");
+        return -1;
+      }
   }
   for (int64_t c = 0; c < ncol; ++c) {
     const float cmp = dynamic_k_range ? tropp[c] : tropp_min;
@@ -125,8 +145,10 @@ extern "C" int qcoh_predict_OH_with_XGB(const char *xgb_fname, int icount, int j
   const float *xx_pred = nullptr;
   rc = XGBoosterPredict(xx_bst, xx_dmtrx, 0, 0, 0, &xx_pred_len, &xx_pred);
   if (rc != 0 || xx_pred_len != (bst_ulong)xx_prediction_count) {
+    const std::string why = rc != 0 ? std::string(XGBGetLastError()) : "XGBoosterPredict_f returned the wrong number of predictions";  // (:359)
     XGDMatrixFree(xx_dmtrx);
     free(xx_carr);
+    qcoh_internal_set_error(why.c_str());
     return -1;
   }
 

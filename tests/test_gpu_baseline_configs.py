@@ -45,11 +45,19 @@ def c90(oracle, prod_model_path):
 
 
 def _leaf_and_margin(capi, booster, x, missing=-999.0):
-    d = capi.DMatrix(x, missing)
-    leaf = booster.predict(d, option_mask=2)
-    k_leaf = capi.last_predict_kernel()
-    margin = booster.predict(d, option_mask=1)
-    k_margin = capi.last_predict_kernel()
+    """Leaf ids, margins and values of one matrix, with the kernel family that served the first two.  The
+    prediction pipelined into XGDMatrixCreateFromMat is switched off so that every predict is its own launch."""
+    capi.set_param("speculate", 0)
+    try:
+        d = capi.DMatrix(x, missing)
+        leaf = booster.predict(d, option_mask=2)
+        k_leaf = capi.last_predict_kernel()
+        margin = booster.predict(d, option_mask=1)
+        k_margin = capi.last_predict_kernel()
+        d.free()
+    finally:
+        capi.set_param("speculate", 1)
+    d = capi.DMatrix(x, missing)  # pipelined create + speculative predict: what the reference's call sequence gets
     value = booster.predict(d, option_mask=0)
     d.free()
     return leaf, margin, value, k_leaf, k_margin
@@ -106,7 +114,7 @@ def test_c90_fused_run1_production_booster(capi, c90, prod_model_path):
     fields, om = c90["fields"], c90["om"]
     from oracle import cpu as oracle
 
-    ref = oracle.run1(om, fields, synth.MAPL, want_features=False)
+    ref = oracle.run1(om, fields, synth.MAPL, want_features=True)
     km, ncol = fields["T"].shape
     b = capi.Booster(prod_model_path)
     oh = capi.OhRun1(b, ncol, km, synth.MAPL)

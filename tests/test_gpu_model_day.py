@@ -39,7 +39,7 @@ def test_model_day(capi, oracle, grid, source, spinup):
     imports["PLE_avg24"] = (base["PLE"] * np.float32(0.999)).astype(np.float32)
     if spinup:  # the coupler hands an all-zero field during the first 24 hours (:1313-1316)
         imports["T_avg24"] = np.zeros_like(base["T"])
-    use_inst = bool(capi.lib().qcoh_use_inst_values(source, float(imports["T_avg24"][0, 0, 0])))
+    use_inst = bool(capi.lib().qcoh_use_inst_values(source, float(imports["T_avg24"].flat[0])))
     assert use_inst == (source == 3 and spinup)
     chosen = {}
     for f in SEL:

@@ -14,7 +14,11 @@ b = capi.Booster(bench.booster_path())
 x = synth.quick_features(synth.raw_fields(a.grid))
 hx = capi.pinned_empty(x.shape); hx[:] = x
 print("rows", x.shape[0], "GB", x.nbytes / 1e9, flush=True)
-for spec, chunk, src, name in ((0, 0, hx, "pinned"), (1, 0, hx, "pinned"), (1, 1 << 19, hx, "pinned"), (0, 0, x, "pageable"), (1, 0, x, "pageable")):
+import os as _os
+cases = ((0, 0, hx, "pinned"), (1, 0, hx, "pinned"), (1, 1 << 19, hx, "pinned"), (0, 0, x, "pageable"), (1, 0, x, "pageable"))
+if _os.environ.get("PAGEABLE_ONLY"):
+    cases = ((1, 0, hx, "pinned"), (1, 0, x, "pageable"), (1, 1 << 18, x, "pageable"), (1, 1 << 17, x, "pageable"))
+for spec, chunk, src, name in cases:
     capi.set_param("speculate", spec); capi.set_param("chunk_rows", chunk)
     print(name, flush=True)
     for it in range(a.iters):

@@ -105,7 +105,9 @@ def time_predict(b, dX):
     capi.timer_start()
     for _ in range(a.iters):
         b.predict_device(dX, out, exp10=True, scale=0.85)
-    return capi.timer_stop() / a.iters
+    ms = capi.timer_stop() / a.iters
+    state["kernel"] = capi.last_predict_kernel()
+    return ms
 
 
 def model_file(t, d):
@@ -128,7 +130,7 @@ def row(b, dX, hx, ms, **extra):
         duo_mb, shift, has_dl = None, None, None
     r = dict(trees=info.num_trees, max_depth=info.max_depth, nodes=int(info.num_nodes), nodes8_mb=round(info.num_nodes * 8 / 1e6, 1),
              duo_mb=None if duo_mb is None else round(duo_mb, 1), duo_blk_shift=shift, visits_per_cell=round(visits, 1),
-             kernel=capi.last_predict_kernel(), ms=round(ms, 3), cells_per_s=ncell / (ms * 1e-3), hbm_gbs=round(gbs, 1),
+             kernel=state.get("kernel"), ms=round(ms, 3), cells_per_s=ncell / (ms * 1e-3), hbm_gbs=round(gbs, 1),
              hbm_frac=round(gbs / peak, 4), **extra)  # fmt: skip
     print(json.dumps(r), flush=True)
     return r
