@@ -145,7 +145,8 @@ int qcoh_dmatrix_device_ptr(DMatrixHandle handle, float **out_dev);
 int qcoh_dmatrix_upload(DMatrixHandle handle, const float *host_rows, bst_ulong row0, bst_ulong nrows);
 int qcoh_dmatrix_seal(DMatrixHandle handle);
 /* The device form of a sealed matrix (what the predict kernels read): order-preserving integer keys in
- * feature-major tiles of 256 rows, Xt[tile][col][256] uint32 (DESIGN.md "Data layout"); for inspection / tests. */
+ * feature-major tiles of 256 rows, Xt[tile][1 + col][256] uint32; word-row 0 of a tile is its row order (rows without
+ * a missing entry first; original row index | has_missing << 8) (DESIGN.md "Data layout"); for inspection / tests. */
 int qcoh_dmatrix_tiles_ptr(DMatrixHandle handle, const uint32_t **out_dev, uint64_t *num_tiles);
 
 /* Export transform fused into the predict kernel's epilogue (OH_GridCompMod.F90:369,1569):

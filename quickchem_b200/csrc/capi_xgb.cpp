@@ -109,26 +109,31 @@ bool duo_wanted(const Booster *b) {
   return kDuoDefault && g.tun.variant == 0 && g.tun.park != 0 && g.tun.top_levels < 0 && g.tun.ilp == 0 && g.tun.minb == 0;
 }
 void sync_const_top(Booster *b, bool allow_duo, int tree0, int ntree) {
-  b->dev.const_top_levels = 0, b->dev.duo_ready = 0, b->dev.const_tree0 = tree0, b->dev.const_ntree = 0;
-  // hold as many trees from tree0 on as fit, so that calls with different ntree_limit do not thrash the table
-  const int hold = std::min(b->dev.ntree - tree0, kConstTreesMax);
-  if (ntree < 0) ntree = hold;
-  if (ntree <= 0 || ntree > hold) return;
+  b->dev.const_top_levels = 0, b->dev.duo_ready = 0, b->dev.const_tree0 = 0, b->dev.const_ntree = 0;
+  if (ntree < 0) ntree = std::min(b->dev.ntree - tree0, kConstTreesMax);
+  if (ntree <= 0 || ntree > kConstTreesMax || tree0 + ntree > b->dev.ntree) return;
+  // The table holds a window of up to kConstTreesMax trees: the aligned window around the request when the request
+  // fits in it (so that ranges of one forest and calls with different ntree_limit share an upload), else one that
+  // starts at the request.
+  int w0 = tree0 - tree0 % kConstTreesMax;
+  if (tree0 + ntree > w0 + kConstTreesMax) w0 = tree0;
+  const int hold = std::min(b->dev.ntree - w0, kConstTreesMax);
   auto holds = [&](int layout) {
-    return g_const_top_owner == b->version && g_const_top_levels == layout && g_const_tree0 == tree0 && g_const_ntree >= ntree;
+    return g_const_top_owner == b->version && g_const_top_levels == layout && g_const_tree0 <= tree0 &&
+           tree0 + ntree <= g_const_tree0 + g_const_ntree;
   };
   if (allow_duo && duo_wanted(b)) {
     if (!holds(kConstDuo)) {
       g_const_top_owner = 0;
-      if (upload_const_duo(b->duo.top_xy.data() + (size_t)tree0 * (2u << kDuoTop), b->duo.tree_slot.data() + tree0, hold, g.stream) ==
+      if (upload_const_duo(b->duo.top_xy.data() + (size_t)w0 * (2u << kDuoTop), b->duo.tree_slot.data() + w0, hold, g.stream) ==
           cudaSuccess) {
-        g_const_top_owner = b->version, g_const_top_levels = kConstDuo, g_const_tree0 = tree0, g_const_ntree = hold;
+        g_const_top_owner = b->version, g_const_top_levels = kConstDuo, g_const_tree0 = w0, g_const_ntree = hold;
       } else {
         (void)cudaGetLastError();
       }
     }
     if (holds(kConstDuo)) {
-      b->dev.duo_ready = 1, b->dev.const_ntree = g_const_ntree;
+      b->dev.duo_ready = 1, b->dev.const_tree0 = g_const_tree0, b->dev.const_ntree = g_const_ntree;
       return;
     }
   }
@@ -136,13 +141,13 @@ void sync_const_top(Booster *b, bool allow_duo, int tree0, int ntree) {
   if (want <= 0) return;
   if (!holds(want)) {
     g_const_top_owner = 0;
-    if (upload_const_top(b->dev_nodes_host.data(), b->flat.tree_offset.data() + tree0, hold, want, g.stream) != cudaSuccess) {
+    if (upload_const_top(b->dev_nodes_host.data(), b->flat.tree_offset.data() + w0, hold, want, g.stream) != cudaSuccess) {
       (void)cudaGetLastError();
       return;  // does not fit: the kernel runs without the table
     }
-    g_const_top_owner = b->version, g_const_top_levels = want, g_const_tree0 = tree0, g_const_ntree = hold;
+    g_const_top_owner = b->version, g_const_top_levels = want, g_const_tree0 = w0, g_const_ntree = hold;
   }
-  b->dev.const_top_levels = want, b->dev.const_ntree = g_const_ntree;
+  b->dev.const_top_levels = want, b->dev.const_tree0 = g_const_tree0, b->dev.const_ntree = g_const_ntree;
 }
 
 // One prediction = one launch per range of kConstTreesMax trees: the tables are re-filled between the launches
@@ -159,8 +164,9 @@ void launch_predict_chunked(Booster *b, PredictArgs a, bool allow_duo, cudaStrea
     }
     return;
   }
-  for (int t0 = 0; t0 < t_end; t0 += kConstTreesMax) {
-    const int n = std::min(kConstTreesMax, t_end - t0);
+  const int range = g.tun.range_trees > 0 ? std::min(g.tun.range_trees, kConstTreesMax) : kConstTreesMax;
+  for (int t0 = 0; t0 < t_end; t0 += range) {
+    const int n = std::min(range, t_end - t0);
     sync_const_top(b, allow_duo, t0, n);
     PredictArgs c = a;
     c.tree_begin = t0, c.tree_end = t0 + n;
@@ -393,7 +399,7 @@ static void create_pipelined(DMatrix *d, const float *data, Booster *b) {
       CU(cudaMemcpyAsync(X + r0 * ncol, src, bytes, cudaMemcpyHostToDevice, g.copy_stream));
     }
     // chunks start on tile boundaries (chunk_rows is a multiple of 256)
-    CU(launch_seal_tiles(X + r0 * ncol, nr, (int)ncol, d->missing, Xt + r0 * ncol, fl + c, g.copy_stream));
+    CU(launch_seal_tiles(X + r0 * ncol, nr, (int)ncol, d->missing, Xt + tile_offset_words(r0, ncol), fl + c, g.copy_stream));
     CU(cudaMemcpyAsync(hfl + c, fl + c, sizeof(int), cudaMemcpyDeviceToHost, g.copy_stream));
     CU(cudaEventRecord(chunk_event(2 * c), g.copy_stream));
   };
@@ -407,7 +413,7 @@ static void create_pipelined(DMatrix *d, const float *data, Booster *b) {
     }
     if (!spec) return;
     PredictArgs a;
-    a.Xt = Xt + r0 * ncol, a.nrow = nr, a.ncol = (int32_t)ncol;
+    a.Xt = Xt + tile_offset_words(r0, ncol), a.nrow = nr, a.ncol = (int32_t)ncol;
     a.has_missing = ((hfl[c] & 1) || ncol < b->host.num_feature) ? 1 : 0;
     a.tree_begin = 0, a.tree_end = (int32_t)b->host.trees.size(), a.out_stride = a.tree_end;
     a.out = sdev + r0;
@@ -819,6 +825,7 @@ int qcoh_set_param(const char *name, const char *value) {
   else if (n == "duo") g.tun.duo = v;
   else if (n == "duo_mask") g.tun.duo_mask = v;
   else if (n == "persist") g.tun.persist = v;
+  else if (n == "range_trees") g.tun.range_trees = v;
   else if (n == "speculate") g.speculate = v;
   else if (n == "chunk_rows") g.chunk_rows = v > 0 ? ((uint64_t)v + 255) / 256 * 256 : (1ull << 21);
   else throw Error("qcoh_set_param: unknown parameter '" + n + "'");

@@ -185,27 +185,27 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 // shared-memory bank-conflict wavefronts on the LSU data pipe, profiles/README.md v4).
 template <int NBUF>
 struct TilePipe {
-  uint32_t smem0, bar0, buf_bytes, tile_bytes;
+  uint32_t smem0, bar0, buf_bytes, tile_bytes, src_skip, dst_skip;
   const uint32_t *Xt;
-  uint64_t ntile, tile;
+  uint64_t ntile, tile, tile_stride;
   uint32_t it;
   __device__ __forceinline__ void issue(uint64_t t, int b) const {
-    if (tile_bytes) {
-      mbar_expect_tx(bar0 + 8u * b, tile_bytes);
-      bulk_g2s(smem0 + buf_bytes * b, Xt + t * (uint64_t)(tile_bytes / 4), tile_bytes, bar0 + 8u * b);
-    } else {
-      mbar_expect_tx(bar0 + 8u * b, 0u);
-    }
+    mbar_expect_tx(bar0 + 8u * b, tile_bytes);
+    if (tile_bytes) bulk_g2s(smem0 + buf_bytes * b + dst_skip, Xt + t * tile_stride + src_skip, tile_bytes, bar0 + 8u * b);
   }
-  // slots the matrix does not have are missing (xgboost FVec::Fill leaves them flagged); slot nfeat is the
-  // key-0 slot leaves point at.  Written once per buffer: the bulk copies only touch slots 0..ncol-1.
-  __device__ __forceinline__ void begin(uint32_t *smem, unsigned long long *bars, const PredictArgs &a, int nfeat, int tid) {
+  // A buffer is [row order | nfeat feature slots | key-0 slot], 1 KB each.  Slots the matrix does not have are
+  // missing (xgboost FVec::Fill leaves them flagged); the last slot is the key-0 slot leaves point at.  Both are
+  // written once per buffer: the bulk copies only touch the order slot (with_order) and slots 0..ncol-1.
+  __device__ __forceinline__ void begin(uint32_t *smem, unsigned long long *bars, const PredictArgs &a, int nfeat, bool with_order, int tid) {
     smem0 = (uint32_t)__cvta_generic_to_shared(smem), bar0 = (uint32_t)__cvta_generic_to_shared(bars);
-    buf_bytes = (uint32_t)(nfeat + 1) * kStride * 4u, tile_bytes = (uint32_t)a.ncol * kStride * 4u;
+    buf_bytes = (uint32_t)(nfeat + 2) * kStride * 4u;
+    tile_stride = (uint64_t)(a.ncol + 1) * kStride;
+    tile_bytes = (uint32_t)(a.ncol + (with_order ? 1 : 0)) * kStride * 4u;
+    src_skip = with_order ? 0u : (uint32_t)kStride, dst_skip = with_order ? 0u : (uint32_t)kStride * 4u;
     Xt = a.Xt, ntile = (a.nrow + kTileRows - 1) / kTileRows, tile = blockIdx.x, it = 0;
 #pragma unroll
     for (int b = 0; b < NBUF; ++b) {
-      uint32_t *k = smem + (size_t)b * (nfeat + 1) * kStride;
+      uint32_t *k = smem + (size_t)b * (nfeat + 2) * kStride + kStride;
       for (int c = a.ncol; c < nfeat; ++c) k[c * kStride + tid] = kKeyMissing;
       k[nfeat * kStride + tid] = 0u;
     }
@@ -218,7 +218,7 @@ struct TilePipe {
     if (tid == 0 && tile < ntile) issue(tile, 0);
   }
   __device__ __forceinline__ bool more() const { return tile < ntile; }
-  // returns the shared address of this iteration's tile
+  // returns the shared address of this iteration's buffer (its row-order slot; the feature slots follow 1 KB later)
   __device__ __forceinline__ uint32_t acquire(int tid) {
     const int cur = NBUF == 2 ? (int)(it & 1u) : 0;
     if (tid == 0) {
@@ -246,7 +246,8 @@ struct TilePipe {
 __global__ void __launch_bounds__(kTileRows) seal_tiles_kernel(const float *__restrict__ X, uint64_t nrow, int ncol, float missing,
                                                                int check_inf, uint32_t *__restrict__ Xt, int *flags) {
   extern __shared__ __align__(16) float srows[];  // [256][ld] row-major, ld odd: the per-thread row reads are conflict-free
-  const int tid = threadIdx.x;
+  __shared__ int warp_clean[kTileRows / 32];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int ld = ncol | 1;
   const uint64_t r0 = (uint64_t)blockIdx.x * kTileRows;
   const uint64_t left = nrow - r0;
@@ -266,24 +267,46 @@ __global__ void __launch_bounds__(kTileRows) seal_tiles_kernel(const float *__re
     for (int i = tid; i < n; i += kTileRows) srows[(i / ncol) * ld + (i % ncol)] = __ldg(src + i);
   }
   __syncthreads();
-  uint32_t *__restrict__ dst = Xt + (size_t)blockIdx.x * (size_t)ncol * kTileRows + tid;
+  // pass 1: does my row hold a missing entry?  (rows past the end of the matrix count as clean; never stored)
   int fl = 0;
-  for (int c = 0; c < ncol; ++c) {
-    uint32_t k = 0u;  // rows past the end of the matrix: any key (their results are never stored)
-    if (tid < nr) {
+  if (tid < nr) {
+    for (int c = 0; c < ncol; ++c) {
       const float x = srows[tid * ld + c];
-      k = float_key(x);
-      if (x != x || x == missing) k = kKeyMissing, fl |= 1;
+      if (x != x || x == missing) fl |= 1;
       if (check_inf && isinf(x)) fl |= 2;
     }
-    dst[(size_t)c * kTileRows] = k;  // 1 KB per column, coalesced
+  }
+  // row order: clean rows first, rows with a missing entry last, both in their original order (stable)
+  const unsigned clean_mask = __ballot_sync(0xffffffffu, !(fl & 1));
+  if (lane == 0) warp_clean[wid] = __popc(clean_mask);
+  __syncthreads();
+  int clean_before = 0, clean_total = 0;
+#pragma unroll
+  for (int w = 0; w < kTileRows / 32; ++w) {
+    const int cw = warp_clean[w];
+    clean_total += cw;
+    if (w < wid) clean_before += cw;
+  }
+  const int my_clean_rank = clean_before + __popc(clean_mask & ((1u << lane) - 1u));
+  const int pos = (fl & 1) ? clean_total + (tid - my_clean_rank) : my_clean_rank;
+  uint32_t *__restrict__ tile = Xt + (size_t)blockIdx.x * (size_t)(ncol + 1) * kTileRows;
+  tile[pos] = (uint32_t)tid | ((uint32_t)(fl & 1) << 8);
+  // pass 2: my row's keys, column by column, to my position (1 KB per column; coalesced where the order is the identity)
+  uint32_t *__restrict__ dst = tile + kTileRows + pos;
+  for (int c = 0; c < ncol; ++c) {
+    uint32_t k = 0u;
+    if (tid < nr) {
+      const float x = srows[tid * ld + c];
+      k = (x != x || x == missing) ? kKeyMissing : float_key(x);
+    }
+    dst[(size_t)c * kTileRows] = k;
   }
   fl = __reduce_or_sync(0xffffffffu, fl);
-  if ((tid & 31) == 0 && fl) atomicOr(flags, fl);
+  if (lane == 0 && fl) atomicOr(flags, fl);
 }
 
 cudaError_t launch_seal_tiles(const float *X, uint64_t nrow, int ncol, float missing, uint32_t *Xt, int *flags, cudaStream_t s) {
-  if (nrow == 0 || ncol == 0) return cudaSuccess;
+  if (nrow == 0) return cudaSuccess;
   const uint64_t ntile = tile_count(nrow);
   if (ntile > 0x7fffffffull) return cudaErrorInvalidConfiguration;
   const size_t smem = (size_t)kTileRows * (size_t)(ncol | 1) * sizeof(float);
@@ -364,19 +387,28 @@ __device__ __forceinline__ void walk_group(const uint2 *__restrict__ nodes, cuda
       }
     }
   }
-  for (int d = CTOP; d <= depth; ++d) {
+  auto fetch = [&](int j) {
+    if ((TEXMODE >> j) & 1)
+      nd[j] = tex1Dfetch<uint2>(tex, (int)idx[j]);
+    else
+      nd[j] = __ldg(nodes + idx[j]);
+  };
+  for (int d = CTOP; d < depth; ++d) {
 #pragma unroll
     for (int j = 0; j < ILP; ++j) {
       if (!PARK || rel[j] != 0u) {
-        if ((TEXMODE >> j) & 1)
-          nd[j] = tex1Dfetch<uint2>(tex, (int)idx[j]);
-        else
-          nd[j] = __ldg(nodes + idx[j]);
+        fetch(j);
         visit(j);
       }
       // keep "still walking" in the rel register only (one ISETP per level instead of predicate shuffling)
       if (PARK) asm volatile("" : "+r"(rel[j]));
     }
+  }
+  // level `depth` holds only leaves: the last fetch reads the leaf a lane stands on — its value is all that is needed
+  if (depth >= CTOP) {
+#pragma unroll
+    for (int j = 0; j < ILP; ++j)
+      if (!PARK || rel[j] != 0u) fetch(j);
   }
 #pragma unroll
   for (int j = 0; j < ILP; ++j) xbits[j] = nd[j].x;
@@ -453,16 +485,21 @@ __device__ __forceinline__ void walk_group_duo(const uint4 *__restrict__ recs, c
   // gather is predicated (a lane that has reached its terminal record stops fetching and keeps it); the
   // arithmetic below runs unconditionally, phase by phase across the ILP trees, so that the trees'
   // dependent chains interleave: on a terminal record (w3 == 0) it reads feature 0 and leaves walking at 0.
-  for (int d = CTOP; d <= depth + 1; d += 2) {
-#pragma unroll
-    for (int j = 0; j < ILP; ++j) {
-      if (walking[j] != 0u) {
-        if ((TEXMODE >> j) & 1)
-          r[j] = tex1Dfetch<uint4>(tex4, (int)idx[j]);
-        else
-          r[j] = __ldg(recs + idx[j]);
-      }
+  auto gather = [&](int j) {
+    if (walking[j] != 0u) {
+      if ((TEXMODE >> j) & 1)
+        r[j] = tex1Dfetch<uint4>(tex4, (int)idx[j]);
+      else
+        r[j] = __ldg(recs + idx[j]);
     }
+  };
+  // Records rooted at the deepest level a walk of these trees can reach (depth, or depth + 1 for an odd depth) are
+  // all terminal: the last iteration is the gather alone — its arithmetic would only confirm w3 == 0.  For the
+  // depth-18 booster that is one eighth of the record arithmetic and of its feature fetches; for a depth-6 forest half.
+  int d = CTOP;
+  for (; d + 2 <= depth + 1; d += 2) {
+#pragma unroll
+    for (int j = 0; j < ILP; ++j) gather(j);
     uint32_t kv0[ILP], kv[ILP], right1[ILP];
 #pragma unroll
     for (int j = 0; j < ILP; ++j) {
@@ -502,6 +539,8 @@ __device__ __forceinline__ void walk_group_duo(const uint4 *__restrict__ recs, c
       asm volatile("" : "+r"(walking[j]));
     }
   }
+#pragma unroll
+  for (int j = 0; j < ILP; ++j) gather(j);
 #pragma unroll
   for (int j = 0; j < ILP; ++j) xbits[j] = r[j].x, ids[j] = r[j].y;
 }
@@ -559,18 +598,38 @@ __device__ __forceinline__ void row_result(const DeviceForest &f, const PredictA
   }
 }
 
+// A launch on a matrix with missing entries reads the tile's row order (kernels.hpp): thread tid walks the row at
+// position tid — clean rows first — and a warp whose 32 rows are all clean takes the walk without the
+// default-direction test.  Returns the row's index in the matrix; `hm` = this warp needs the test.
+template <bool HAS_MISSING>
+__device__ __forceinline__ uint64_t tile_row(uint32_t buf, uint64_t tile, int tid, bool absent_columns, bool &hm) {
+  uint32_t orig = (uint32_t)tid;
+  hm = false;
+  if (HAS_MISSING) {
+    const uint32_t p = lds_u32(buf + 4u * (uint32_t)tid);
+    orig = p & 0xFFu;
+    hm = __any_sync(0xffffffffu, (p >> 8) & 1u) || absent_columns;
+  }
+  return tile * kTileRows + orig;
+}
+
 template <int ILP, int MINB, int TEXMODE, bool HAS_MISSING, bool PRED_LEAF, int NBUF>
 __global__ void __launch_bounds__(kBlock, MINB) predict_tiles_kernel(DeviceForest f, PredictArgs a) {
   extern __shared__ __align__(128) uint32_t skey[];
   __shared__ __align__(8) unsigned long long bars[NBUF];
   const int tid = threadIdx.x;
   TilePipe<NBUF> pipe;
-  pipe.begin(skey, bars, a, f.nfeat, tid);
+  pipe.begin(skey, bars, a, f.nfeat, HAS_MISSING, tid);
   while (pipe.more()) {
-    const uint32_t my = pipe.acquire(tid) + 4u * (uint32_t)tid;
-    const uint64_t row = pipe.tile * kTileRows + tid;
+    const uint32_t buf = pipe.acquire(tid);
+    const uint32_t my = buf + 4u * (uint32_t)(kStride + tid);
+    bool hm;
+    const uint64_t row = tile_row<HAS_MISSING>(buf, pipe.tile, tid, a.ncol < f.nfeat, hm);
     row_result<PRED_LEAF>(f, a, row, row < a.nrow, [&](auto &&emit) {
-      forest_walk_duo<ILP, TEXMODE, HAS_MISSING>(f, my, a.tree_begin, a.tree_end, emit);
+      if (HAS_MISSING && hm)
+        forest_walk_duo<ILP, TEXMODE, true>(f, my, a.tree_begin, a.tree_end, emit);
+      else
+        forest_walk_duo<ILP, TEXMODE, false>(f, my, a.tree_begin, a.tree_end, emit);
     });
     pipe.release(tid);
   }
@@ -582,14 +641,18 @@ __global__ void __launch_bounds__(kBlock, MINB) predict_tiles_nodes8_kernel(Devi
   __shared__ __align__(8) unsigned long long bars[1];
   const int tid = threadIdx.x;
   TilePipe<1> pipe;
-  pipe.begin(skey, bars, a, f.nfeat, tid);
+  pipe.begin(skey, bars, a, f.nfeat, HAS_MISSING, tid);
   while (pipe.more()) {
-    const uint32_t my = pipe.acquire(tid) + 4u * (uint32_t)tid;
-    const uint64_t row = pipe.tile * kTileRows + tid;
+    const uint32_t buf = pipe.acquire(tid);
+    const uint32_t my = buf + 4u * (uint32_t)(kStride + tid);
+    bool hm;
+    const uint64_t row = tile_row<HAS_MISSING>(buf, pipe.tile, tid, a.ncol < f.nfeat, hm);
     row_result<PRED_LEAF>(f, a, row, row < a.nrow, [&](auto &&emit) {
-      forest_walk<ILP, HAS_MISSING, PARK, TEXMODE, CTOP>(f, my, a.tree_begin, a.tree_end, [&](int t, uint32_t xb, uint32_t idx) {
-        emit(t, xb, PRED_LEAF ? (uint32_t)__ldg(f.orig_id + idx) : 0u);
-      });
+      auto leaf = [&](int t, uint32_t xb, uint32_t idx) { emit(t, xb, PRED_LEAF ? (uint32_t)__ldg(f.orig_id + idx) : 0u); };
+      if (HAS_MISSING && hm)
+        forest_walk<ILP, true, PARK, TEXMODE, CTOP>(f, my, a.tree_begin, a.tree_end, leaf);
+      else
+        forest_walk<ILP, false, PARK, TEXMODE, CTOP>(f, my, a.tree_begin, a.tree_end, leaf);
     });
     pipe.release(tid);
   }
@@ -685,7 +748,7 @@ static int sm_count() {
 
 template <class K>
 static cudaError_t launch_tiles(K k, const DeviceForest &f, const PredictArgs &a, int nbuf, int persistent_ctas_per_sm, cudaStream_t s) {
-  const size_t smem = (size_t)nbuf * kStride * (size_t)(f.nfeat + 1) * sizeof(uint32_t);
+  const size_t smem = (size_t)nbuf * kStride * (size_t)(f.nfeat + 2) * sizeof(uint32_t);
   const uint64_t ntile = tile_count(a.nrow);
   uint64_t grid = ntile;
   if (persistent_ctas_per_sm > 0) grid = std::min<uint64_t>(ntile, (uint64_t)sm_count() * persistent_ctas_per_sm);
@@ -739,7 +802,7 @@ cudaError_t launch_predict(const DeviceForest &f, const PredictArgs &a, const Tu
     QC_DUO(4, 6, 0xA) QC_DUO(4, 6, 0xE) QC_DUO(4, 6, 0xF) QC_DUO(3, 6, 0x6) QC_DUO(3, 6, 0x2) QC_DUO(6, 5, 0x2A) QC_DUO(8, 4, 0xEE)
     // shallow forests (the HBM-bound end): more resident CTAs, fewer trees in flight, LSU-only gathers
     QC_DUO(4, 6, 0x100) QC_DUO(3, 6, 0x100) QC_DUO(2, 6, 0x100) QC_DUO(2, 6, 0x2) QC_DUO(6, 5, 0x100) QC_DUO(6, 5, 0x14)
-    QC_DUO(4, 7, 0x100) QC_DUO(4, 7, 0xA) QC_DUO(3, 7, 0x100) QC_DUO(3, 7, 0x2) QC_DUO(2, 7, 0x100) QC_DUO(5, 6, 0x100) QC_DUO(5, 6, 0xA)
+    QC_DUO(6, 5, 0x3F) QC_DUO(4, 7, 0x100) QC_DUO(4, 7, 0xA) QC_DUO(3, 7, 0x100) QC_DUO(3, 7, 0x2) QC_DUO(2, 7, 0x100) QC_DUO(5, 6, 0x100) QC_DUO(5, 6, 0xA)
 #undef QC_DUO
 #endif
     if (persist) return launch_duo<kDuoIlp, kPersistCtasPerSm, kDuoTexMask, 2>(f, a, kPersistCtasPerSm, s);

@@ -32,13 +32,20 @@ struct DeviceForest {
 constexpr int kConstTreesMax = 480;
 
 // The device form of a DMatrix: order-preserving integer KEYS (kernels.cu) in feature-major tiles of 256 rows,
-// Xt[tile][col][256] — what a CTA's transposed shared-memory tile holds, so that a tile arrives with one bulk
+// Xt[tile][1 + col][256] — what a CTA's transposed shared-memory tile holds, so that a tile arrives with one bulk
 // async copy (TMA) and needs no staging arithmetic.  Missing entries (NaN or == missing) are key 0xFFFFFFFF.
+// Word-row 0 of a tile is its ROW ORDER: within a tile the rows without a missing entry come first (stable), the
+// rows with one last; word p of the order row = original row index in the tile | has_missing << 8.  A predict launch
+// on a matrix with missing entries reads it, so that a warp whose 32 rows are all clean walks without the
+// default-direction test: what missing entries cost is proportional to the rows that have them.  (A clean matrix has
+// the identity order and its launches skip that word-row.)
 // Built by seal_tiles from the row-major float matrix, like libxgboost builds its SparsePage in
 // XGDMatrixCreateFromMat (OH_GridCompMod.F90:347).
 constexpr int kTileRows = 256;
 inline uint64_t tile_count(uint64_t nrow) { return (nrow + kTileRows - 1) / kTileRows; }
-inline size_t tile_words(uint64_t nrow, uint64_t ncol) { return (size_t)tile_count(nrow) * (size_t)ncol * kTileRows; }
+inline size_t tile_words(uint64_t nrow, uint64_t ncol) { return (size_t)tile_count(nrow) * (size_t)(ncol + 1) * kTileRows; }
+// words from the start of Xt to the tile that holds row `row0` (a multiple of 256)
+inline size_t tile_offset_words(uint64_t row0, uint64_t ncol) { return (size_t)(row0 / kTileRows) * (size_t)(ncol + 1) * kTileRows; }
 
 struct PredictArgs {
   const uint32_t *Xt = nullptr;  // key tiles, device
@@ -65,7 +72,8 @@ struct Tunables {
   int minb = 0;      // min resident CTAs per SM the kernel is compiled for (register budget)
   int duo = -1;      // two-level records: -1 = default, 0 = off, 1 = on
   int duo_mask = 0;  // (experiment) texture-pipe tree mask of the two-level kernel, 0 = default
-  int persist = -1;  // persistent double-buffered tile loop: -1 = auto (shallow forests), 0 = off, 1 = on
+  int persist = -1;  // persistent double-buffered tile loop: 1 = on (default off, see kernels.cu)
+  int range_trees = 0;  // trees per launch (<= kConstTreesMax): 0 = default
 };
 
 constexpr bool kDuoDefault = true;  // two-level records by default when the booster qualifies

@@ -128,25 +128,39 @@ def test_c90_fused_run1_production_booster(capi, c90, prod_model_path):
 
 
 def test_seal_builds_key_tiles(capi):
-    """XGDMatrixCreateFromMat's device form: Xt[tile][col][256] order-preserving keys, missing = 0xFFFFFFFF."""
+    """XGDMatrixCreateFromMat's device form: Xt[tile][1 + col][256] order-preserving keys, missing = 0xFFFFFFFF; word-row
+    0 of a tile is its row order — rows without a missing entry first, both groups in their original order."""
     rng = np.random.default_rng(1)
-    for nrow, ncol in ((1000, 27), (256, 27), (1, 5), (700, 12), (513, 32 - 1)):
+    for nrow, ncol, pmiss in ((1000, 27, 0.02), (256, 27, 0.0), (1, 5, 0.5), (700, 12, 0.05), (513, 32 - 1, 0.3), (4096, 27, 0.001)):
         x = rng.normal(0, 1, (nrow, ncol)).astype(np.float32)
-        x[rng.random(x.shape) < 0.05] = -999.0
-        x[rng.random(x.shape) < 0.05] = np.nan
+        x[rng.random(x.shape) < pmiss] = -999.0
+        x[rng.random(x.shape) < pmiss] = np.nan
         x[0, 0] = -0.0
         x.flat[1 % x.size] = np.float32(1e-42)
         d = capi.DMatrix(x)
         p, nt = capi.vp(), capi.u64()
         capi.check(capi.lib().qcoh_dmatrix_tiles_ptr(d.handle, C.byref(p), C.byref(nt)))
         assert nt.value == (nrow + 255) // 256
-        t = np.empty((nt.value, ncol, 256), np.uint32)
+        t = np.empty((nt.value, ncol + 1, 256), np.uint32)
         capi.check(capi.lib().qcoh_memcpy_d2h(t.ctypes.data_as(capi.vp), p, t.nbytes))
         b = (x + np.float32(0)).view(np.uint32)
         key = b ^ np.where(b >> 31, np.uint32(0xFFFFFFFF), np.uint32(0x80000000))
-        key = np.where(np.isnan(x) | (x == np.float32(-999.0)), np.uint32(0xFFFFFFFF), key)
-        got = t.transpose(0, 2, 1).reshape(-1, ncol)[:nrow]
-        assert np.array_equal(got, key), (nrow, ncol)
+        miss = np.isnan(x) | (x == np.float32(-999.0))
+        key = np.where(miss, np.uint32(0xFFFFFFFF), key)
+        rowmiss = miss.any(axis=1)
+        for ti in range(nt.value):
+            order = t[ti, 0]
+            orig, flag = (order & 0xFF).astype(np.int64), (order >> 8) & 1
+            assert sorted(orig) == list(range(256))  # a permutation of the tile's rows
+            nr = min(256, nrow - ti * 256)
+            real = orig < nr
+            rm = np.zeros(256, bool)
+            rm[real] = rowmiss[ti * 256 + orig[real]]
+            assert np.array_equal(flag.astype(bool), rm)
+            assert np.all(np.diff(flag.astype(np.int64)) >= 0)  # clean rows first ...
+            assert np.all(np.diff(orig[flag == 0]) > 0) and np.all(np.diff(orig[flag == 1]) > 0)  # ... both stable
+            got = t[ti, 1:, :].T  # [position][col]
+            assert np.array_equal(got[real], key[ti * 256 + orig[real]]), (nrow, ncol, ti)
         d.free()
 
 

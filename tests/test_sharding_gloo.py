@@ -66,3 +66,23 @@ def test_two_rank_sharding_matches_single_rank(oracle, small_model_path, tmp_pat
     w = (fields["PLE"][1:].astype(np.float64) - fields["PLE"][:-1]) * (pl > fields["TROPP"][None, :])
     expect = np.array([(ref["OH"].astype(np.float64) * w).sum(), w.sum()])
     assert np.allclose(got["part"], expect, rtol=1e-10, atol=0)
+
+
+def test_bench_fields_do_not_depend_on_the_sharding():
+    """bench.py's synthetic state is a function of the global column only (synth.raw_fields_blocked), so that
+    1, 2, 4 and 8 ranks compute the same global OH and the bench line's checksum can be compared across N."""
+    import bench
+    from quickchem_b200 import synth
+
+    for grid, worlds in ((12, (1, 2, 4, 8)), (24, (1, 2, 3, 4, 6, 8))):
+        whole = synth.raw_fields_blocked(grid, 7)
+        assert whole["T"].shape == (72, 6 * grid * grid) and whole["PLE"].shape[0] == 73
+        for world in worlds:
+            parts = []
+            for rank in range(world):
+                j0, j1 = bench.shard_rows(grid, rank, world)
+                parts.append(synth.raw_fields_blocked(grid, 7, j0, j1))
+            assert bench.shard_rows(grid, 0, world)[0] == 0 and bench.shard_rows(grid, world - 1, world)[1] == 6 * grid
+            for k in whole:
+                assert np.array_equal(np.concatenate([p[k] for p in parts], axis=-1), whole[k]), (grid, world, k)
+    assert not np.array_equal(synth.raw_fields_blocked(12, 7)["T"], synth.raw_fields_blocked(12, 8)["T"])
