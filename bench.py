@@ -177,7 +177,8 @@ def run_reference(args):
 
 
 def workload_config(grid, world):
-    return {"workload": f"C{grid}x{KM}L OH prediction, {6 * grid * grid * KM} cells, dense X[Nx27] f32 (BASELINE configs[2])",
+    which = {90: "configs[1]", 360: "configs[2]", 720: "configs[3]", 180: "configs[4]"}.get(grid, "other grid")
+    return {"workload": f"C{grid}x{KM}L OH prediction, {6 * grid * grid * KM} cells, dense X[Nx27] f32 (BASELINE {which})",
             "booster": f"{BOOSTER['n_trees']} trees, max depth {BOOSTER['max_depth']}, 27 features (synthetic, seeded)",
             "sharding": f"{world} rank(s), contiguous column blocks, no halo",
             "cache": "inputs (>= 0.75 GB per GPU) exceed the 126 MB L2; forest stays L2-resident by design"}  # fmt: skip

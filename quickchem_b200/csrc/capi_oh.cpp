@@ -303,7 +303,7 @@ int qcoh_oh_run1(qcoh_oh_handle h, const qcoh_run1_in *in, qcoh_run1_out *out) {
     upload(o->booster);
     sync_const_top(o->booster, true);  // tiles walk the two-level records when the booster qualifies
     CU(cudaMemsetAsync(r.OH_ML, 0, n3 * 4, g.stream));  // self%OH_ML = 0.0 (:1559)
-    const bool too_many_trees = o->booster->dev.ntree > kConstTreesMax;  // chunked launches need the matrix form
+    const bool too_many_trees = o->booster->dev.ntree > kRangeTrees;  // ranged launches need the matrix form
     if (npred && !out->X && !too_many_trees) {
       // fused: pack (:303-345) + create (:347) + predict (:356) + 10**x (:369) * OHscale (:1569) in one
       // kernel reading the SoA fields; the [N x 27] matrix is never formed

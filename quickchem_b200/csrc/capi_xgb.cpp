@@ -71,7 +71,7 @@ void upload(Booster *b) {
   }
   // two-level records, when every tree qualifies
   if (b->dev.tex4) cudaDestroyTextureObject(b->dev.tex4);
-  b->dev.tex4 = 0, b->dev.recs = nullptr, b->dev.duo_ready = 0, b->dev.duo_has_dl = 0, b->dev.duo_blk_mul = 0;
+  b->dev.tex4 = 0, b->dev.recs = nullptr, b->dev.duo_ready = 0, b->dev.duo_has_dl = 0, b->dev.duo_blk_mul = 0, b->dev.duo_shallow = 0;
   if (b->duo.ok && b->duo.num_slots() > 0 && b->duo.num_slots() < ((int64_t)1 << 27)) {
     const size_t ns = (size_t)b->duo.num_slots();
     CU(cudaMemcpy(b->d_recs.need(ns), b->duo.rec.data(), ns * 16, cudaMemcpyHostToDevice));
@@ -87,6 +87,7 @@ void upload(Booster *b) {
     CU(cudaCreateTextureObject(&b->dev.tex4, &rd, &td, nullptr));
     b->dev.recs = b->d_recs.p;
     b->dev.duo_has_dl = b->duo.has_default_bits ? 1 : 0;
+    b->dev.duo_shallow = (int64_t)ns * 16 < kShallowRecBytesPerTree * std::max<int64_t>(1, b->dev.ntree) ? 1 : 0;
     b->dev.duo_blk_mul = 1u << (32 - b->duo.blk_shift);
   }
   b->uploaded = true;
@@ -150,8 +151,8 @@ void sync_const_top(Booster *b, bool allow_duo, int tree0, int ntree) {
   b->dev.const_top_levels = want, b->dev.const_tree0 = g_const_tree0, b->dev.const_ntree = g_const_ntree;
 }
 
-// One prediction = one launch per range of kConstTreesMax trees: the tables are re-filled between the launches
-// (stream-ordered) and the float32 partial sum travels through `out`, so the sum order — tree 0, 1, 2, ... — and
+// One prediction = one launch per range of kRangeTrees trees (kernels.hpp; the tables hold kConstTreesMax and are
+// re-filled, stream-ordered, when a range leaves them) and the float32 partial sum travels through `out`, so the sum order — tree 0, 1, 2, ... — and
 // with it every bit of the result is the same as in a single launch.
 void launch_predict_chunked(Booster *b, PredictArgs a, bool allow_duo, cudaStream_t s) {
   const int t_end = a.tree_end;
@@ -164,7 +165,7 @@ void launch_predict_chunked(Booster *b, PredictArgs a, bool allow_duo, cudaStrea
     }
     return;
   }
-  const int range = g.tun.range_trees > 0 ? std::min(g.tun.range_trees, kConstTreesMax) : kConstTreesMax;
+  const int range = g.tun.range_trees > 0 ? std::min(g.tun.range_trees, kConstTreesMax) : kRangeTrees;
   for (int t0 = 0; t0 < t_end; t0 += range) {
     const int n = std::min(range, t_end - t0);
     sync_const_top(b, allow_duo, t0, n);

@@ -806,6 +806,7 @@ cudaError_t launch_predict(const DeviceForest &f, const PredictArgs &a, const Tu
 #undef QC_DUO
 #endif
     if (persist) return launch_duo<kDuoIlp, kPersistCtasPerSm, kDuoTexMask, 2>(f, a, kPersistCtasPerSm, s);
+    if (f.duo_shallow && t.ilp == 0) return launch_duo<4, 6, 0xA, 1>(f, a, 0, s);  // kernels.hpp kShallowRecBytesPerTree
     return launch_duo<kDuoIlp, kDuoMinBlocks, kDuoTexMask, 1>(f, a, 0, s);
   }
   // ---- 8-byte depth-ordered nodes: 4 trees in flight per thread; levels 0..3 of every tree from constant

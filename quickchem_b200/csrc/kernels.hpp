@@ -24,12 +24,21 @@ struct DeviceForest {
   int32_t nfeat = 0;
   int32_t max_depth = 0;
   int64_t num_nodes = 0;
-  int64_t sum_depth = 0;                 // sum over trees of the deepest leaf's depth (picks the launch shape)
+  int64_t sum_depth = 0;                 // sum over trees of the deepest leaf's depth
+  int duo_shallow = 0;                   // records average < kShallowRecBytesPerTree per tree (picks the launch shape)
   float base_score = 0.f;
 };
 
-// How many trees the constant-memory tables hold at once (4 levels x 16 entries per tree in 61 440 B).
+// How many trees the constant-memory tables hold at once (4 levels x 16 entries per tree in 61 440 B), and how
+// many of them one launch walks.  Measured (profiles/README.md "trees per launch"): warps drift apart through a
+// forest, and when a launch walks hundreds of trees their tops and shallow records no longer share the constant
+// cache and L1 — 500 trees x depth 10 take 75 ms in one 480-tree launch and 25 ms in launches of 120 (the tile
+// stream is re-read per launch: 0.23 ms of the 5 ms a 120-tree range takes at C180).
 constexpr int kConstTreesMax = 480;
+constexpr int kRangeTrees = 120;
+// A forest whose records average less than this per tree (depth <= ~7) is "shallow": 4 trees in flight and 6
+// resident CTAs instead of 6 and 5 (100 trees x depth 6: 3.2 ms against 8.0 ms).
+constexpr int64_t kShallowRecBytesPerTree = 4096;
 
 // The device form of a DMatrix: order-preserving integer KEYS (kernels.cu) in feature-major tiles of 256 rows,
 // Xt[tile][1 + col][256] — what a CTA's transposed shared-memory tile holds, so that a tile arrives with one bulk

@@ -191,8 +191,9 @@ def test_persistent_prefetch_loop_matches(capi, oracle, tmp_path, small_forest, 
 
 
 def test_more_than_480_trees_stay_on_the_fast_path(capi, oracle, tmp_path):
-    """The constant-memory tables hold 480 trees; a bigger forest is walked in ranges of 480 trees, the float32
-    partial sum carried through the output buffer, so it stays on the two-level records and keeps the sum order."""
+    """A launch walks at most 120 trees (the constant-memory tables hold 480 and are re-filled when a range leaves
+    them); the float32 partial sum is carried through the output buffer, so a forest of any size stays on the
+    two-level records and keeps the sum order."""
     f = synth.random_forest_structure(1100, 7, seed=77, p_leaf=0.1)
     p = str(tmp_path / "many.model")
     xgbmodel.write_legacy_binary(f, p)
@@ -202,9 +203,9 @@ def test_more_than_480_trees_stay_on_the_fast_path(capi, oracle, tmp_path):
     b = capi.Booster(p)
     n0 = capi.kernel_launches("duo")
     got = b.predict(capi.DMatrix(x))
-    assert capi.kernel_launches("duo") == n0 + 3 and capi.last_predict_kernel() == "duo"  # 480 + 480 + 140 trees
+    assert capi.kernel_launches("duo") == n0 + 10 and capi.last_predict_kernel() == "duo"  # 9 x 120 + 20 trees
     assert np.array_equal(got.view(np.uint32), om.predict(x).view(np.uint32))
-    for lim in (1, 480, 481, 960, 1000):
+    for lim in (1, 120, 121, 480, 481, 960, 1000):
         assert np.array_equal(b.predict(capi.DMatrix(x), ntree_limit=lim).view(np.uint32),
                               om.predict(x, ntree_limit=lim).view(np.uint32)), lim  # fmt: skip
     assert np.array_equal(b.predict(capi.DMatrix(x), option_mask=2), om.predict(x, option_mask=2))

@@ -171,6 +171,15 @@ def test_run1_persistent_oh_ml_and_device_fields(capi, oracle, small_model_path)
     assert np.array_equal(got["OH"].view(np.uint32), expect.astype(np.float32).view(np.uint32))
 
 
+def test_run1_rejects_a_malformed_date(capi, small_model_path):
+    fields = synth.raw_fields(4)
+    oh = capi.OhRun1(capi.Booster(small_model_path), fields["T"].shape[1], 72, synth.MAPL)
+    for nymd in (20221301, 20220230, 20220000, -5):
+        with pytest.raises(capi.QcohError, match="yyyymmdd"):
+            oh.run(oh.make_in(fields, nymd=nymd))
+    oh.run(oh.make_in(fields, nymd=20240229))  # a leap day is a date
+
+
 def test_run1_needs_a_boost_call_first(capi, small_model_path):
     fields = synth.raw_fields(4)
     oh = capi.OhRun1(capi.Booster(small_model_path), fields["T"].shape[1], 72, synth.MAPL)
@@ -230,6 +239,19 @@ def test_host_mirror_predict_OH_with_XGB(capi, oracle, small_model_path):
     OH2 = np.zeros_like(OH_ML)
     assert capi.predict_OH_with_XGB("/nonexistent/ignored.model", 6, ncol // 6, km, False, 4000.0, pl_mod,
                                     fields["TROPP"], bb, OH2) == 0  # fmt: skip
+    assert np.array_equal(OH_ML, OH2)
+    # the reference's _ASSERT (:287-288) has a message here too, and XGBGetLastError carries it
+    low = fields["TROPP"].copy()
+    low[3] = 3000.0
+    assert capi.predict_OH_with_XGB(small_model_path, 6, ncol // 6, km, False, 4000.0, pl_mod, low, bb, OH2) == -1
+    assert "Minimum tropopause pressure is not low enough" in capi.last_error()
+    capi.lib().qcoh_predict_OH_reset()
+    # a failing INIT (:242-271) reports the loader's reason, frees what it created and can be retried
+    for _ in range(3):
+        assert capi.predict_OH_with_XGB("/nonexistent/model.bin", 6, ncol // 6, km, False, 4000.0, pl_mod,
+                                        fields["TROPP"], bb, OH2) == -1  # fmt: skip
+        assert "Opening" in capi.last_error()
+    assert capi.predict_OH_with_XGB(small_model_path, 6, ncol // 6, km, False, 4000.0, pl_mod, fields["TROPP"], bb, OH2) == 0
     assert np.array_equal(OH_ML, OH2)
     capi.lib().qcoh_predict_OH_reset()
 
