@@ -99,3 +99,41 @@ def _neighbours(thr):
             vals.append(cur)
             cur = np.nextafter(cur, F32(np.inf), dtype=np.float32)
     return vals
+
+
+@pytest.mark.parametrize("duo", [1, 0], ids=["duo", "nodes8"])
+def test_rows_with_missing_entries_in_any_number(capi, oracle, tmp_path, duo):
+    """The seal kernel orders each tile's rows (clean first) so that only warps holding rows with missing entries
+    take the default-direction walk: any number of such rows per tile — none, one, a warp's worth +-1, all — in the
+    first, a middle and the ragged last tile must give the oracle's leaf ids and sums, on both layouts."""
+    from quickchem_b200 import synth
+
+    rng = np.random.default_rng(77)
+    forest = synth.random_forest_structure(9, 11, seed=6, p_leaf=0.12)
+    p = str(tmp_path / "m.model")
+    xgbmodel.write_legacy_binary(forest, p)
+    om = oracle.Model(p)
+    b = capi.Booster(p)
+    nrow = 3 * 256 + 77
+    capi.set_param("duo", duo)
+    try:
+        for nmiss in (0, 1, 31, 32, 33, 255, 256, 300, nrow):
+            x = rng.normal(0, 1, (nrow, 27)).astype(np.float32)
+            rows = rng.choice(nrow, nmiss, replace=False)
+            for r in rows:  # one to three missing entries per chosen row, NaN or -999.0
+                cols = rng.choice(27, int(rng.integers(1, 4)), replace=False)
+                x[r, cols] = np.where(rng.random(len(cols)) < 0.5, np.nan, F32(-999.0))
+            if nmiss == 300:
+                x[512:768] = rng.normal(0, 1, (256, 27)).astype(np.float32)  # one tile stays clean inside a missing matrix
+            d = capi.DMatrix(x)
+            assert np.array_equal(b.predict(d).view(np.uint32), om.predict(x).view(np.uint32)), nmiss
+            fam = ("duo" if duo else "nodes8") + ("_missing" if nmiss else "")
+            assert capi.last_predict_kernel() == fam
+            assert np.array_equal(b.predict(d, option_mask=2), om.predict(x, option_mask=2)), nmiss
+            for persist in (1,) if duo else ():
+                capi.set_param("persist", persist)
+                assert np.array_equal(b.predict(d, ntree_limit=7).view(np.uint32), om.predict(x, ntree_limit=7).view(np.uint32))
+                capi.set_param("persist", -1)
+    finally:
+        capi.set_param("duo", -1)
+        capi.set_param("persist", -1)
