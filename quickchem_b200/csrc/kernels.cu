@@ -893,21 +893,16 @@ cudaError_t launch_oh_state(const Run1Dev &r, cudaStream_t s) {
 // needs its own forward chain x(k) + x(k+1) + ... (SURVEY.md hard part 6).  One thread per
 // column keeps KB chains per field in registers and sweeps the column once per block of KB
 // levels; the UP sums are a running prefix.  aod and PL_BST are kept (DIAG_AOD, DIAG_PL).
-// SMEM: the column's TAUCLW / TAUCLI / aod are parked in shared memory by the first pass ([field][level][thread]:
-// conflict-free, and private to the thread, so no barrier), and the km / KB sweeps of the second pass read them
-// there instead of re-reading the column from L2 nine times.
+// (Tried: parking the column's TAUCLW / TAUCLI / aod in shared memory for the second pass — 108 KB per 128-column CTA
+// leaves 8 warps per SM and the streaming first pass then starves: the fused Run1 step grew from 43.3 to 44.2 ms at
+// C360.  The sweeps of the second pass hit L2.)
 constexpr int KB = 8;
-constexpr int kSumsCols = 128;
-template <bool SMEM>
-__global__ void __launch_bounds__(kSumsCols) oh_sums_kernel(Run1Dev r) {
-  extern __shared__ float scol[];  // SMEM: [3][km][kSumsCols]
-  const int tid = threadIdx.x;
-  const int c = blockIdx.x * kSumsCols + tid;
+__global__ void __launch_bounds__(128) oh_sums_kernel(Run1Dev r) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= r.ncol) return;
   const int nc = r.ncol, km = r.km;
   float *__restrict__ aod = r.aod;
   float *wdn = r.sums[0], *idn = r.sums[1], *iup = r.sums[2], *wup = r.sums[3], *aup = r.sums[4], *adn = r.sums[5];
-  float *sw = scol + tid, *si = sw + (size_t)km * kSumsCols, *sa = si + (size_t)km * kSumsCols;
   if (r.lat_deg) r.lat_deg[c] = __fmul_rn(r.LATS[c], r.r2d);         // latarr (:1444)
   if (r.so3) r.so3[c] = __fadd_rn(r.GMITO3[c], -r.GMITTO3[c]);       // stratO3 (:1446)
   // pass 1: aod and the UP prefixes
@@ -930,11 +925,9 @@ __global__ void __launch_bounds__(kSumsCols) oh_sums_kernel(Run1Dev r) {
     // double(thick) * double(sc) is exact (24 + 24 bits), so rounding it to REAL equals the
     // correctly rounded float32 product
     const float a = __fmul_rn(thick, sc);
-    const float w = r.TAUCLW[e], i = r.TAUCLI[e];
     aod[e] = a;
-    if (SMEM) sw[k * kSumsCols] = w, si[k * kSumsCols] = i, sa[k * kSumsCols] = a;
-    s_iup = __fadd_rn(s_iup, i);
-    s_wup = __fadd_rn(s_wup, w);
+    s_iup = __fadd_rn(s_iup, r.TAUCLI[e]);
+    s_wup = __fadd_rn(s_wup, r.TAUCLW[e]);
     s_aup = __fadd_rn(s_aup, a);
     iup[e] = s_iup, wup[e] = s_wup, aup[e] = s_aup;
     z_up = z_dn;
@@ -946,9 +939,7 @@ __global__ void __launch_bounds__(kSumsCols) oh_sums_kernel(Run1Dev r) {
     for (int j = 0; j < KB; ++j) cw[j] = ci[j] = ca[j] = 0.f;
     for (int kk = k0; kk < km; ++kk) {
       const size_t e = (size_t)kk * nc + c;
-      const float w = SMEM ? sw[kk * kSumsCols] : r.TAUCLW[e];
-      const float i = SMEM ? si[kk * kSumsCols] : r.TAUCLI[e];
-      const float a = SMEM ? sa[kk * kSumsCols] : aod[e];
+      const float w = r.TAUCLW[e], i = r.TAUCLI[e], a = aod[e];
 #pragma unroll
       for (int j = 0; j < KB; ++j)
         if (k0 + j <= kk) {
@@ -967,15 +958,7 @@ __global__ void __launch_bounds__(kSumsCols) oh_sums_kernel(Run1Dev r) {
 }
 
 cudaError_t launch_oh_sums(const Run1Dev &r, cudaStream_t s) {
-  const size_t smem = (size_t)3 * r.km * kSumsCols * sizeof(float);
-  const unsigned grid = (unsigned)((r.ncol + kSumsCols - 1) / kSumsCols);
-  if (smem <= 113 * 1024) {  // two CTAs per SM (72 levels: 108 KB)
-    cudaError_t e = cudaFuncSetAttribute(oh_sums_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    oh_sums_kernel<true><<<grid, kSumsCols, smem, s>>>(r);
-  } else {
-    oh_sums_kernel<false><<<grid, kSumsCols, 0, s>>>(r);
-  }
+  oh_sums_kernel<<<(r.ncol + 127) / 128, 128, 0, s>>>(r);
   return QC_LAUNCHED();
 }
 
