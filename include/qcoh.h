@@ -14,8 +14,10 @@
  *      (OH_GridCompMod.F90:1232-1599): feature assembly, prediction, export transform and the
  *      build-defined global-mean diagnostic without ever forming the [N x 27] matrix on the host.
  *
- * Plain pointers and sizes only.  Thread model: one host thread per process per GPU (as the
- * reference: `SAVE` booster, OH_GridCompMod.F90:182,209); the last-error string is thread-local.
+ * Plain pointers and sizes only.  Thread model: a host thread is one "rank" bound to one GPU — one process per
+ * GPU (as the reference: `SAVE` booster, OH_GridCompMod.F90:182,209), or one process with one host thread per GPU.
+ * All library state (device context, handles, buffer pools, model cache, last-error string) is thread-local: a
+ * handle belongs to the thread that created it, and a second thread cannot bind to a GPU that already has one.
  */
 #ifndef QCOH_H
 #define QCOH_H
@@ -242,7 +244,7 @@ int qcoh_oh_get_booster(qcoh_oh_handle h, BoosterHandle *out);
  * GrADS-style expansion of the tokens %y4 %y2 %m1 %m2 %mc %Mc %MC %d1 %d2 %h1 %h2 %n2 %j3 (%% = '%');
  * nymd = yyyymmdd, nhms = hhmmss.  Fails on an unknown token or when `cap` (including the NUL) is too small. */
 int qcoh_expand_template(const char *pattern, int nymd, int nhms, char *out, size_t cap);
-/* Process-wide cache of parsed + uploaded boosters keyed by file name: the first request for a name loads
+/* Per-thread (= per GPU) cache of parsed + uploaded boosters keyed by file name: the first request for a name loads
  * it, later ones return the same handle.  Handles belong to the cache (XGBoosterFree on one fails); a month
  * of the production forest is ~30 MB of HBM (both node layouts), so all twelve stay resident. */
 int qcoh_model_cache_get(const char *fname, BoosterHandle *out);
