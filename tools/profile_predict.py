@@ -41,7 +41,7 @@ def timeit(label):
     for _ in range(a.iters):
         b.predict_device(d, out, exp10=True, scale=0.85)
     ms = capi.timer_stop() / a.iters
-    print(f"{label}: {ms:.3f} ms/launch  {x.shape[0] / ms / 1e3:.4g} cells/s", flush=True)
+    print(f"{label}: {ms:.3f} ms/launch  {x.shape[0] / ms / 1e3:.4g} Mcells/s", flush=True)
     return ms
 
 
