@@ -237,10 +237,11 @@ static bool is_pinned_host(const void *p) {
   return a.type == cudaMemoryTypeHost;
 }
 
-// Multi-threaded memcpy (pageable host -> pinned staging) on a persistent pool: a Fortran ALLOCATE gives pageable
+// Multi-threaded copy (pageable host -> pinned staging) on a persistent pool: a Fortran ALLOCATE gives pageable
 // memory (xx_carr, OH_GridCompMod.F90:306), and one core's memcpy (~10 GB/s) is far below PCIe 5 x16.  The
-// workers are created once and parked on a condition variable; spawning threads per chunk cost more than the copy
-// of a small chunk.  Threads: the cores this process may use divided by the ranks sharing the node.
+// workers are created once and parked on a condition variable; the calling thread does not copy — it issues the
+// CUDA work of the previous chunk while the workers stage the next one.  Threads: the cores this process may use
+// divided by the ranks sharing the node.
 // Copy into the pinned staging ring with non-temporal stores: a plain memcpy reads every destination line before
 // overwriting it (read-for-ownership), i.e. 3 transfers per byte where the staging copy needs 2, and the staging
 // data is only ever read back by the DMA engine.  QCOH_COPY_NT=0 selects memcpy.
@@ -272,26 +273,33 @@ class CopyPool {
     static CopyPool p;
     return p;
   }
-  void copy(void *dst, const void *src, size_t bytes) {
-    std::lock_guard<std::mutex> one_caller(callers_);  // threads driving different GPUs share the workers
-    const unsigned nt = (unsigned)workers_.size() + 1;
-    if (nt == 1 || bytes < ((size_t)4 << 20)) {
+  // start copying on the workers and return; wait() blocks until that copy is complete.  One copy at a time per
+  // process (threads driving different GPUs take turns: begin() holds the pool until wait()).
+  void begin(void *dst, const void *src, size_t bytes) {
+    callers_.lock();
+    if (workers_.empty() || bytes < ((size_t)4 << 20)) {
       stream_copy((char *)dst, (const char *)src, bytes);
+      inline_done_ = true;
       return;
     }
-    const size_t per = (bytes / nt + 4095) / 4096 * 4096;
+    inline_done_ = false;
+    const unsigned nt = (unsigned)workers_.size();
     {
       std::lock_guard<std::mutex> lk(m_);
-      dst_ = (char *)dst, src_ = (const char *)src, bytes_ = bytes, per_ = per;
-      pending_ = (unsigned)workers_.size();
+      dst_ = (char *)dst, src_ = (const char *)src, bytes_ = bytes, per_ = (bytes / nt + 4095) / 4096 * 4096;
+      pending_ = nt;
       ++generation_;
     }
     cv_.notify_all();
-    part(nt - 1);  // the caller copies the last part
-    std::unique_lock<std::mutex> lk(m_);
-    done_.wait(lk, [&] { return pending_ == 0; });
   }
-  unsigned threads() const { return (unsigned)workers_.size() + 1; }
+  void wait() {
+    if (!inline_done_) {
+      std::unique_lock<std::mutex> lk(m_);
+      done_.wait(lk, [&] { return pending_ == 0; });
+    }
+    callers_.unlock();
+  }
+  unsigned threads() const { return (unsigned)workers_.size(); }
 
  private:
   CopyPool() {
@@ -305,7 +313,7 @@ class CopyPool {
     if (const char *lw = getenv("LOCAL_WORLD_SIZE")) share = (unsigned)std::max(1, atoi(lw));
     unsigned nt = std::max(1u, std::min(32u, cores / share));
     if (const char *e = getenv("QCOH_COPY_THREADS")) nt = (unsigned)std::max(1, atoi(e));
-    for (unsigned t = 0; t + 1 < nt; ++t) workers_.emplace_back([this, t] { run(t); });
+    for (unsigned t = 0; t < nt; ++t) workers_.emplace_back([this, t] { run(t); });
   }
   ~CopyPool() {
     {
@@ -341,10 +349,8 @@ class CopyPool {
   size_t bytes_ = 0, per_ = 0;
   unsigned pending_ = 0;
   uint64_t generation_ = 0;
-  bool stop_ = false;
+  bool stop_ = false, inline_done_ = false;
 };
-static void parallel_memcpy(void *dst, const void *src, size_t bytes) { CopyPool::get().copy(dst, src, bytes); }
-
 constexpr int kStageSlots = 3;
 static thread_local PinBuf<float> g_stage[kStageSlots];
 static thread_local cudaEvent_t g_stage_free[kStageSlots] = {nullptr, nullptr, nullptr};
@@ -384,20 +390,24 @@ static void create_pipelined(DMatrix *d, const float *data, Booster *b) {
     for (int s = 0; s < kStageSlots; ++s)
       if (!g_stage_free[s]) CU(cudaEventCreateWithFlags(&g_stage_free[s], cudaEventDisableTiming));
   int flags = 0;
+  // pageable source: stage_begin(c) starts the workers on chunk c (into ring slot c % 3, once its previous H2D has
+  // drained), stage_end() waits for them; issue(c) queues H2D(c) -> seal(c) -> flag D2H(c)
+  auto stage_begin = [&](size_t c) {
+    const uint64_t r0 = c * cr, nr = std::min(cr, nrow - r0);
+    const int s = (int)(c % kStageSlots);
+    float *st = g_stage[s].need(cr * ncol);
+    if (c >= (size_t)kStageSlots) CU(cudaEventSynchronize(g_stage_free[s]));
+    CopyPool::get().begin(st, data + r0 * ncol, nr * ncol * sizeof(float));
+  };
   auto issue = [&](size_t c) {
     const uint64_t r0 = c * cr, nr = std::min(cr, nrow - r0);
     const size_t bytes = nr * ncol * sizeof(float);
-    const float *src = data + r0 * ncol;
     if (!pinned) {
       const int s = (int)(c % kStageSlots);
-      float *st = g_stage[s].need(cr * ncol);
-      if (c >= (size_t)kStageSlots) CU(cudaEventSynchronize(g_stage_free[s]));  // its previous H2D has drained
-      parallel_memcpy(st, src, bytes);
-      src = st;
-      CU(cudaMemcpyAsync(X + r0 * ncol, src, bytes, cudaMemcpyHostToDevice, g.copy_stream));
+      CU(cudaMemcpyAsync(X + r0 * ncol, g_stage[s].p, bytes, cudaMemcpyHostToDevice, g.copy_stream));
       CU(cudaEventRecord(g_stage_free[s], g.copy_stream));
     } else {
-      CU(cudaMemcpyAsync(X + r0 * ncol, src, bytes, cudaMemcpyHostToDevice, g.copy_stream));
+      CU(cudaMemcpyAsync(X + r0 * ncol, data + r0 * ncol, bytes, cudaMemcpyHostToDevice, g.copy_stream));
     }
     // chunks start on tile boundaries (chunk_rows is a multiple of 256)
     CU(launch_seal_tiles(X + r0 * ncol, nr, (int)ncol, d->missing, Xt + tile_offset_words(r0, ncol), fl + c, g.copy_stream));
@@ -423,11 +433,24 @@ static void create_pipelined(DMatrix *d, const float *data, Booster *b) {
     CU(cudaStreamWaitEvent(g.d2h_stream, chunk_event(2 * c + 1), 0));
     CU(cudaMemcpyAsync(shost + r0, sdev + r0, nr * sizeof(float), cudaMemcpyDeviceToHost, g.d2h_stream));
   };
-  // pinned source: every copy can be queued up front; pageable: stage two chunks ahead of the GPU (three slots)
-  const size_t lookahead = pinned ? nchunk : 2;
-  for (size_t c = 0; c < nchunk + lookahead; ++c) {
-    if (c < nchunk) issue(c);
-    if (c >= lookahead && c - lookahead < nchunk) process(c - lookahead);
+  if (pinned) {  // every copy can be queued up front
+    for (size_t c = 0; c < nchunk; ++c) issue(c);
+    for (size_t c = 0; c < nchunk; ++c) process(c);
+  } else {  // the workers stage chunk c + 1 while this thread queues the CUDA work of chunk c and predicts chunk c - 2
+    struct PoolGuard {  // an exception between begin() and wait() must not leave the pool locked
+      bool busy = false;
+      ~PoolGuard() {
+        if (busy) CopyPool::get().wait();
+      }
+    } pool;
+    if (nchunk) stage_begin(0), pool.busy = true;
+    for (size_t c = 0; c < nchunk; ++c) {
+      CopyPool::get().wait(), pool.busy = false;
+      if (c + 1 < nchunk) stage_begin(c + 1), pool.busy = true;
+      issue(c);
+      if (c >= 2) process(c - 2);
+    }
+    for (size_t c = nchunk >= 2 ? nchunk - 2 : 0; c < nchunk; ++c) process(c);
   }
   CU(cudaStreamSynchronize(g.copy_stream));  // the borrowed host buffer has been read completely
   d->hflags = flags;
@@ -726,7 +749,7 @@ int XGDMatrixCreateFromFile(const char *fname, int silent, DMatrixHandle *out) {
 // =====================================================================================
 // (2) qcoh_* extension
 // =====================================================================================
-const char *qcoh_version(void) { return "libqcoh 0.1 (sm_100a)"; }
+const char *qcoh_version(void) { return "libqcoh 0.2 (sm_100a)"; }
 
 int qcoh_device_count(void) {
   int n = 0;
