@@ -530,6 +530,7 @@ int XGDMatrixCreateFromMat(const float *data, bst_ulong nrow, bst_ulong ncol, fl
   API_BEGIN
   if (!out) throw Error("XGDMatrixCreateFromMat: out is NULL");
   if (!data && nrow && ncol) throw Error("XGDMatrixCreateFromMat: data is NULL");
+  if (ncol > kMaxMatrixCols) throw Error("XGDMatrixCreateFromMat: " + std::to_string(ncol) + " columns; libqcoh's tile form holds at most " + std::to_string(kMaxMatrixCols));
   ensure_device();
   std::unique_ptr<DMatrix> d(new DMatrix());
   d->nrow = nrow, d->ncol = ncol, d->missing = missing;
@@ -911,6 +912,7 @@ int qcoh_booster_get_duo_info(BoosterHandle handle, int *blk_shift, int *has_def
 
 int qcoh_dmatrix_create_device(bst_ulong nrow, bst_ulong ncol, float missing, DMatrixHandle *out) {
   API_BEGIN
+  if (ncol > kMaxMatrixCols) throw Error("qcoh_dmatrix_create_device: " + std::to_string(ncol) + " columns; libqcoh's tile form holds at most " + std::to_string(kMaxMatrixCols));
   ensure_device();
   std::unique_ptr<DMatrix> d(new DMatrix());
   d->nrow = nrow, d->ncol = ncol, d->missing = missing;

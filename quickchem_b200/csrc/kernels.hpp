@@ -51,6 +51,7 @@ constexpr int64_t kShallowRecBytesPerTree = 4096;
 // Built by seal_tiles from the row-major float matrix, like libxgboost builds its SparsePage in
 // XGDMatrixCreateFromMat (OH_GridCompMod.F90:347).
 constexpr int kTileRows = 256;
+constexpr uint64_t kMaxMatrixCols = 192;  // seal stages a 256 x ncol tile in shared memory; boosters take <= 31 features anyway
 inline uint64_t tile_count(uint64_t nrow) { return (nrow + kTileRows - 1) / kTileRows; }
 inline size_t tile_words(uint64_t nrow, uint64_t ncol) { return (size_t)tile_count(nrow) * (size_t)(ncol + 1) * kTileRows; }
 // words from the start of Xt to the tile that holds row `row0` (a multiple of 256)

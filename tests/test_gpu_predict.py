@@ -157,6 +157,8 @@ def test_error_behaviour(capi, small_model_path, tmp_path):
         capi.DMatrix(x)  # finite missing + inf data: libxgboost's CreateFromMat fails too
     with pytest.raises(capi.QcohError, match="Number of columns"):
         b.predict(capi.DMatrix(np.zeros((2, 28), np.float32)))
+    with pytest.raises(capi.QcohError, match="columns"):
+        capi.DMatrix(np.zeros((2, 500), np.float32))
     with pytest.raises(capi.QcohError, match="option_mask"):
         b.predict(capi.DMatrix(np.zeros((2, 27), np.float32)), option_mask=4)
     empty = capi.Booster()
